@@ -1,0 +1,654 @@
+// Host-side orchestration of the occupancy network: parameter layout, workspace carving and the
+// stream-ordered launch sequences for forward / backward / sequential decode.  All launches go to the
+// caller's stream; nothing here synchronises.  Mirrors (does not copy) the structure of
+// models/model_core.py:38-81, models/upsample.py:137-295 and models/resnet.py:55-60 of the reference.
+#include <math.h>
+#include <stdarg.h>
+
+#include <vector>
+
+#include "net_kernels.cuh"
+
+using namespace linr;
+
+// ---------------------------------------------------------------------------------------------- errors
+static thread_local char g_err[512] = "";
+void linr_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int linr_sm_count() {
+    static int sm = 0;
+    if (!sm) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm <= 0)
+            sm = 148;
+    }
+    return sm;
+}
+
+// ---------------------------------------------------------------------------------------------- layout
+namespace {
+
+struct BlockL {
+    int A_w, A_b, c00_w, c00_b, c01_w, c01_b, c10_w, c10_b, c11_w, c11_b, c12_w, c12_b, B_w, B_b;
+};
+struct Layout {
+    int S = 0;
+    int emb = 0;
+    int sce_w1[MAXS], sce_b1[MAXS], sce_w2[MAXS], sce_b2[MAXS];
+    BlockL bin;
+    int mlp_w1[8], mlp_b1[8], mlp_w2[8], mlp_b2[8];
+    int pr_w[8], pr_b[8];
+    BlockL ob[7];
+    int conv_first = 0;  // first parameter that is not SCE (embedding + scale MLPs)
+    int total = 0;
+    std::vector<int64_t> offsets;  // one per tensor, parameters() order
+};
+
+// parameters() order of LINR_PCGC_Model (checkpoint contract)
+Layout make_layout(int S) {
+    Layout L;
+    L.S = S;
+    int o = 0;
+    auto take = [&](int n) {
+        L.offsets.push_back(o);
+        int r = o;
+        o += n;
+        return r;
+    };
+    L.emb = take(S * 8);
+    for (int s = 0; s < S; ++s) {
+        L.sce_w1[s] = take(16 * 15);
+        L.sce_b1[s] = take(16);
+        L.sce_w2[s] = take(8 * 16);
+        L.sce_b2[s] = take(8);
+    }
+    L.conv_first = o;
+    auto block = [&](int cin) {
+        BlockL b;
+        b.A_w = take(27 * cin * 8), b.A_b = take(8);
+        b.c00_w = take(27 * 8 * 4), b.c00_b = take(4);
+        b.c01_w = take(27 * 4 * 4), b.c01_b = take(4);
+        b.c10_w = take(8 * 4), b.c10_b = take(4);
+        b.c11_w = take(27 * 4 * 4), b.c11_b = take(4);
+        b.c12_w = take(4 * 4), b.c12_b = take(4);
+        b.B_w = take(27 * 8 * 8), b.B_b = take(8);
+        return b;
+    };
+    L.bin = block(8);
+    for (int k = 0; k < 8; ++k) {
+        L.mlp_w1[k] = take(24 * 8), L.mlp_b1[k] = take(24), L.mlp_w2[k] = take(24), L.mlp_b2[k] = take(1);
+    }
+    for (int k = 0; k < 8; ++k) L.pr_w[k] = take(27 * 8 * 8), L.pr_b[k] = take(8);
+    for (int k = 0; k < 7; ++k) L.ob[k] = block(k + 1);
+    L.total = o;
+    return L;
+}
+
+const Layout &layout_for(int S) {
+    static thread_local Layout cache[MAXS + 1];
+    if (cache[S].S != S) cache[S] = make_layout(S);
+    return cache[S];
+}
+
+// ---------------------------------------------------------------------------------------------- workspace
+struct NetWs {
+    int64_t R = 0;
+    int n_chunks = 0;
+    int64_t chunk = 0;
+    // forward
+    float *f0, *bi_y, *bi_t1, *bi_t0, *bi_t2, *bi_z;
+    float *hh;  // [8][R][8]: hh[0] = g, hh[k] = g + LDFE_{k-1}
+    float *ob_y, *ob_t1, *ob_t0, *ob_t2, *ob_z;  // [7][R][C]
+    float *hc;                                   // [8][R][8]
+    float *dzs;                                  // [8][R]
+    float *bits_partial;
+    // backward
+    float *dc, *dhh, *dg, *g_dz, *g_dt0, *g_dy, *g_dt2, *g_dt1, *df0;
+    float *partial, *sce_rec;
+    bool ok = false;
+    size_t used = 0;
+};
+
+int chunks_for(int64_t R) {
+    int64_t nb = ceil_div64(R, 64);
+    int64_t cap = 2 * (int64_t)linr_sm_count();
+    if (nb > cap) nb = cap;
+    if (nb < 1) nb = 1;
+    return (int)nb;
+}
+
+NetWs carve_net(void *ws, size_t bytes, int64_t R, int train, int P, int S) {
+    NetWs w;
+    w.R = R;
+    w.n_chunks = chunks_for(R);
+    w.chunk = (ceil_div64(R, w.n_chunks) + 15) / 16 * 16;
+    if (w.chunk < 16) w.chunk = 16;
+    WsCursor c(ws, bytes);
+    const size_t r = (size_t)(R > 0 ? R : 1);
+    w.f0 = c.take<float>(r * 8);
+    w.bi_y = c.take<float>(r * 8), w.bi_t1 = c.take<float>(r * 4), w.bi_t0 = c.take<float>(r * 4);
+    w.bi_t2 = c.take<float>(r * 4), w.bi_z = c.take<float>(r * 8);
+    w.hh = c.take<float>(r * 64);
+    w.ob_y = c.take<float>(r * 56), w.ob_t1 = c.take<float>(r * 28), w.ob_t0 = c.take<float>(r * 28);
+    w.ob_t2 = c.take<float>(r * 28), w.ob_z = c.take<float>(r * 56);
+    w.hc = c.take<float>(r * 64);
+    w.dzs = c.take<float>(r * 8);
+    w.bits_partial = c.take<float>((size_t)ceil_div64(r, CONV_TPB) * 8);
+    if (train) {
+        w.dc = c.take<float>(r * 64), w.dhh = c.take<float>(r * 64), w.dg = c.take<float>(r * 8);
+        w.g_dz = c.take<float>(r * 56), w.g_dt0 = c.take<float>(r * 28), w.g_dy = c.take<float>(r * 56);
+        w.g_dt2 = c.take<float>(r * 28), w.g_dt1 = c.take<float>(r * 28);
+        w.df0 = c.take<float>(r * 8);
+        w.partial = c.take<float>((size_t)w.n_chunks * P);
+        w.sce_rec = c.take<float>((size_t)w.n_chunks * S * SCE_REC);
+    }
+    w.ok = c.ok;
+    w.used = c.off;
+    return w;
+}
+
+// ---------------------------------------------------------------------------------------------- launch helpers
+inline Tens T(float *p, int64_t gs, int ld, int off = 0) { return Tens{p, gs, ld, off}; }
+inline Tens TN() { return Tens{nullptr, 0, 0, 0}; }
+
+RowMap map_of(const linr_rows *r) { return RowMap{r->d_anchor, r->ld, r->d_mask, r->n_rows}; }
+
+template <int CIN, int COUT, int MODE>
+void launch_conv(const ConvArgs &a, int G, cudaStream_t s) {
+    if (a.map.n_rows <= 0) return;
+    dim3 grid((unsigned)ceil_div64(a.map.n_rows, CONV_TPB), (unsigned)G);
+    conv27_kernel<CIN, COUT, MODE><<<grid, CONV_TPB, 0, s>>>(a);
+}
+template <int CIN, int COUT>
+void launch_pw(const PwArgs &a, int G, cudaStream_t s) {
+    if (a.n_rows <= 0) return;
+    dim3 grid((unsigned)ceil_div64(a.n_rows, PW_TPB), (unsigned)G);
+    pw_kernel<CIN, COUT><<<grid, PW_TPB, 0, s>>>(a);
+}
+
+ConvArgs conv_args(const RowMap &m, const float *params) {
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.map = m;
+    a.params = params;
+    for (int g = 0; g < MAXG; ++g) a.b_off[g] = -1;
+    a.out_ld = m.n_rows;
+    return a;
+}
+PwArgs pw_args(int64_t n, const float *params) {
+    PwArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_rows = n;
+    a.params = params;
+    for (int g = 0; g < MAXG; ++g) a.b_off[g] = -1;
+    return a;
+}
+
+struct BlockBufs {  // activations of G blocks, group stride = R * C
+    float *y, *t1, *t0, *t2, *z;
+};
+
+// Block(x) = ConvB(IRN(ReLU(ConvA(x))))  (models/upsample.py:88-97, models/resnet.py:55-60)
+// in_bits: input are the low (cin_base + g*cin_step) occupancy bits; else float x [R,8].
+void block_forward(const float *params, const BlockL *L, int G, const RowMap &m, bool in_bits, const uint8_t *occ, int cin_base,
+                   int cin_step, Tens x, const BlockBufs &b, Tens out, Tens res_out, cudaStream_t s) {
+    const int64_t R = m.n_rows;
+    {  // ConvA + ReLU -> y
+        ConvArgs a = conv_args(m, params);
+        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].A_w, a.b_off[g] = L[g].A_b;
+        a.y = T(b.y, R * 8, 8), a.relu = 1;
+        if (in_bits) {
+            a.occ = occ, a.cin_base = cin_base, a.cin_step = cin_step;
+            launch_conv<8, 8, 1>(a, G, s);
+        } else {
+            a.x = x;
+            launch_conv<8, 8, 0>(a, G, s);
+        }
+    }
+    {  // conv1_0 (k=1) + ReLU -> t1
+        PwArgs a = pw_args(R, params);
+        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].c10_w, a.b_off[g] = L[g].c10_b;
+        a.x = T(b.y, R * 8, 8), a.y = T(b.t1, R * 4, 4), a.relu = 1;
+        launch_pw<8, 4>(a, G, s);
+    }
+    {  // conv0_0 + ReLU -> t0
+        ConvArgs a = conv_args(m, params);
+        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].c00_w, a.b_off[g] = L[g].c00_b;
+        a.x = T(b.y, R * 8, 8), a.y = T(b.t0, R * 4, 4), a.relu = 1;
+        launch_conv<8, 4, 0>(a, G, s);
+    }
+    {  // conv0_1 -> z[:, 0:4] = u + y[:, 0:4]
+        ConvArgs a = conv_args(m, params);
+        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].c01_w, a.b_off[g] = L[g].c01_b;
+        a.x = T(b.t0, R * 4, 4), a.y = T(b.z, R * 8, 8, 0), a.res = T(b.y, R * 8, 8, 0);
+        launch_conv<4, 4, 0>(a, G, s);
+    }
+    {  // conv1_1 + ReLU -> t2
+        ConvArgs a = conv_args(m, params);
+        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].c11_w, a.b_off[g] = L[g].c11_b;
+        a.x = T(b.t1, R * 4, 4), a.y = T(b.t2, R * 4, 4), a.relu = 1;
+        launch_conv<4, 4, 0>(a, G, s);
+    }
+    {  // conv1_2 (k=1) -> z[:, 4:8] = v + y[:, 4:8]
+        PwArgs a = pw_args(R, params);
+        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].c12_w, a.b_off[g] = L[g].c12_b;
+        a.x = T(b.t2, R * 4, 4), a.y = T(b.z, R * 8, 8, 4), a.res = T(b.y, R * 8, 8, 4);
+        launch_pw<4, 4>(a, G, s);
+    }
+    {  // ConvB (+ residual g for the LDFE blocks: h_k = g + block, models/upsample.py:213)
+        ConvArgs a = conv_args(m, params);
+        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].B_w, a.b_off[g] = L[g].B_b;
+        a.x = T(b.z, R * 8, 8), a.y = out, a.res = res_out;
+        launch_conv<8, 8, 0>(a, G, s);
+    }
+}
+
+struct BlockGrads {  // scratch of G blocks
+    float *dz, *dt0, *dy, *dt2, *dt1;
+};
+
+template <int CIN, int COUT, int MODE>
+void launch_bwd_w(const RowMap &m, const NetWs &w, int P, const int *w_off, const int *b_off, int G, Tens x, Tens dy,
+                  const uint8_t *occ, int cin_base, int cin_step, cudaStream_t s) {
+    BwdWArgs a;
+    memset(&a, 0, sizeof(a));
+    a.map = m;
+    for (int g = 0; g < G; ++g) a.w_off[g] = w_off[g], a.b_off[g] = b_off[g];
+    a.x = x, a.dy = dy, a.occ = occ, a.cin_base = cin_base, a.cin_step = cin_step;
+    a.partial = w.partial, a.P = P, a.chunk = w.chunk;
+    dim3 grid((unsigned)w.n_chunks, (unsigned)G);
+    conv27_bwd_w_kernel<CIN, COUT, MODE><<<grid, BWDW_TPB, 0, s>>>(a);
+}
+template <int CIN, int COUT>
+void launch_pw_bwd_w(int64_t R, const NetWs &w, int P, const int *w_off, const int *b_off, int G, Tens x, Tens dy, cudaStream_t s) {
+    PwBwdWArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_rows = R;
+    for (int g = 0; g < G; ++g) a.w_off[g] = w_off[g], a.b_off[g] = b_off[g];
+    a.x = x, a.dy = dy, a.partial = w.partial, a.P = P, a.chunk = w.chunk;
+    dim3 grid((unsigned)w.n_chunks, (unsigned)G);
+    pw_bwd_w_kernel<CIN, COUT><<<grid, PWW_TPB, 0, s>>>(a);
+}
+
+// Backward of block_forward for G blocks.  dout: gradient wrt the block output.  If dx.p != null (block_in)
+// the gradient wrt the float input is produced too.
+void block_backward(const float *params, const BlockL *L, int G, const RowMap &m, const NetWs &w, int P, bool in_bits,
+                    const uint8_t *occ, int cin_base, int cin_step, Tens x, const BlockBufs &b, const BlockGrads &gr, Tens dout,
+                    Tens dx, cudaStream_t s) {
+    const int64_t R = m.n_rows;
+    int wo[MAXG], bo[MAXG];
+    auto offs = [&](int BlockL::*pw, int BlockL::*pb) {
+        for (int g = 0; g < G; ++g) wo[g] = L[g].*pw, bo[g] = L[g].*pb;
+    };
+    const Tens y = T(b.y, R * 8, 8), t0 = T(b.t0, R * 4, 4), t1 = T(b.t1, R * 4, 4), t2 = T(b.t2, R * 4, 4), z = T(b.z, R * 8, 8);
+    const Tens dz = T(gr.dz, R * 8, 8), dzl = T(gr.dz, R * 8, 8, 0), dzh = T(gr.dz, R * 8, 8, 4);
+    const Tens dt0 = T(gr.dt0, R * 4, 4), dt1 = T(gr.dt1, R * 4, 4), dt2 = T(gr.dt2, R * 4, 4), dy = T(gr.dy, R * 8, 8);
+
+    // ConvB: dW, then dz = B^T dout
+    offs(&BlockL::B_w, &BlockL::B_b);
+    launch_bwd_w<8, 8, 0>(m, w, P, wo, bo, G, z, dout, nullptr, 0, 0, s);
+    {
+        ConvArgs a = conv_args(m, params);
+        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].B_w;
+        a.flip = 1, a.x = dout, a.y = dz;
+        launch_conv<8, 8, 0>(a, G, s);
+    }
+    // path 0: conv0_1 then conv0_0
+    offs(&BlockL::c01_w, &BlockL::c01_b);
+    launch_bwd_w<4, 4, 0>(m, w, P, wo, bo, G, t0, dzl, nullptr, 0, 0, s);
+    {
+        ConvArgs a = conv_args(m, params);
+        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].c01_w;
+        a.flip = 1, a.x = dzl, a.y = dt0, a.rmask = t0;
+        launch_conv<4, 4, 0>(a, G, s);
+    }
+    offs(&BlockL::c00_w, &BlockL::c00_b);
+    launch_bwd_w<8, 4, 0>(m, w, P, wo, bo, G, y, dt0, nullptr, 0, 0, s);
+    {  // dy = dz (residual) + c00^T dt0
+        ConvArgs a = conv_args(m, params);
+        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].c00_w;
+        a.flip = 1, a.x = dt0, a.y = dy, a.res = dz;
+        launch_conv<4, 8, 0>(a, G, s);
+    }
+    // path 1: conv1_2 (k=1), conv1_1, conv1_0 (k=1)
+    offs(&BlockL::c12_w, &BlockL::c12_b);
+    launch_pw_bwd_w<4, 4>(R, w, P, wo, bo, G, t2, dzh, s);
+    {
+        PwArgs a = pw_args(R, params);
+        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].c12_w;
+        a.transpose = 1, a.x = dzh, a.y = dt2, a.rmask = t2;
+        launch_pw<4, 4>(a, G, s);
+    }
+    offs(&BlockL::c11_w, &BlockL::c11_b);
+    launch_bwd_w<4, 4, 0>(m, w, P, wo, bo, G, t1, dt2, nullptr, 0, 0, s);
+    {
+        ConvArgs a = conv_args(m, params);
+        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].c11_w;
+        a.flip = 1, a.x = dt2, a.y = dt1, a.rmask = t1;
+        launch_conv<4, 4, 0>(a, G, s);
+    }
+    offs(&BlockL::c10_w, &BlockL::c10_b);
+    launch_pw_bwd_w<8, 4>(R, w, P, wo, bo, G, y, dt1, s);
+    {  // dy += c10^T dt1, then the ReLU mask of y
+        PwArgs a = pw_args(R, params);
+        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].c10_w;
+        a.transpose = 1, a.x = dt1, a.y = dy, a.accum = 1, a.rmask = y;
+        launch_pw<4, 8>(a, G, s);
+    }
+    // ConvA
+    offs(&BlockL::A_w, &BlockL::A_b);
+    if (in_bits) launch_bwd_w<8, 8, 1>(m, w, P, wo, bo, G, TN(), dy, occ, cin_base, cin_step, s);
+    else launch_bwd_w<8, 8, 0>(m, w, P, wo, bo, G, x, dy, nullptr, 0, 0, s);
+    if (dx.p) {
+        ConvArgs a = conv_args(m, params);
+        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].A_w;
+        a.flip = 1, a.x = dy, a.y = dx;
+        launch_conv<8, 8, 0>(a, G, s);
+    }
+}
+
+SceArgs sce_args(const float *params, const Layout &L, const linr_rows *rows) {
+    SceArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_rows = rows->n_rows, a.scale_num = L.S, a.params = params, a.emb_off = L.emb;
+    for (int s = 0; s < L.S; ++s) a.w1_off[s] = L.sce_w1[s], a.b1_off[s] = L.sce_b1[s], a.w2_off[s] = L.sce_w2[s], a.b2_off[s] = L.sce_b2[s];
+    a.nbr7 = rows->d_nbr7, a.scale = rows->d_scale, a.scale_fixed = -1;
+    return a;
+}
+
+void head_forward(const float *params, const Layout &L, const RowMap &m, int first_stage, int G, Tens x, float *hc,
+                  const uint8_t *occ, float *probs, uint16_t *cdf, float *dz, float dz_scale, float *bits_partial,
+                  int stage_out_base, cudaStream_t s) {
+    ConvArgs a = conv_args(m, params);
+    for (int g = 0; g < G; ++g) {
+        const int k = first_stage + g;
+        a.w_off[g] = L.pr_w[k], a.b_off[g] = L.pr_b[k];
+        a.w1_off[g] = L.mlp_w1[k], a.b1_off[g] = L.mlp_b1[k], a.w2_off[g] = L.mlp_w2[k], a.b2_off[g] = L.mlp_b2[k];
+    }
+    a.x = x;
+    a.y = hc ? T(hc, m.n_rows * 8, 8) : TN();
+    a.occ = occ, a.stage_base = first_stage, a.stage_out_base = stage_out_base;
+    a.probs = probs, a.cdf = cdf, a.dz = dz, a.dz_scale = dz_scale, a.bits_partial = bits_partial;
+    launch_conv<8, 8, 2>(a, G, s);
+}
+
+int check_rows(const linr_rows *rows, int S, bool need_occ) {
+    LINR_REQUIRE(rows != nullptr, "rows is null");
+    LINR_REQUIRE(S >= 1 && S <= MAXS, "scale_num %d out of range [1,%d]", S, MAXS);
+    LINR_REQUIRE(rows->n_rows >= 0 && rows->n_rows < (1ll << 31) / 64, "n_rows out of range");
+    LINR_REQUIRE(rows->ld >= rows->n_rows, "anchor ld < n_rows");
+    LINR_REQUIRE(rows->n_rows == 0 || (rows->d_anchor && rows->d_mask && rows->d_nbr7 && rows->d_scale), "null row tables");
+    LINR_REQUIRE(!need_occ || rows->n_rows == 0 || rows->d_occ, "occupancy required");
+    return LINR_OK;
+}
+
+}  // namespace
+
+// ============================================================================================== C ABI
+extern "C" {
+
+int linr_version(void) { return 100; }
+const char *linr_last_error(void) { return g_err; }
+
+int linr_device_info(int device, int *sm_count, int64_t *l2_bytes) {
+    int sm = 0, l2 = 0;
+    LINR_CHECK_CUDA(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device));
+    LINR_CHECK_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, device));
+    if (sm_count) *sm_count = sm;
+    if (l2_bytes) *l2_bytes = l2;
+    return LINR_OK;
+}
+
+int64_t linr_param_count(int scale_num) {
+    if (scale_num < 1 || scale_num > MAXS) return -1;
+    return layout_for(scale_num).total;
+}
+int linr_param_offsets(int scale_num, int64_t *h_offsets, int cap) {
+    if (scale_num < 1 || scale_num > MAXS) return LINR_EINVAL;
+    const Layout &L = layout_for(scale_num);
+    for (int i = 0; i < (int)L.offsets.size() && i < cap; ++i) h_offsets[i] = L.offsets[i];
+    return (int)L.offsets.size();
+}
+
+size_t linr_net_ws_bytes(int64_t n_rows, int train) {
+    NetWs w = carve_net(nullptr, ~(size_t)0, n_rows, train, (int)layout_for(MAXS).total, MAXS);
+    return w.used + 4096;
+}
+
+int linr_net_forward(const float *d_params, int scale_num, const linr_rows *rows, int train, float loss_scale,
+                     float *d_probs, uint16_t *d_cdf, double *d_bits, void *d_ws, size_t ws_bytes, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = check_rows(rows, scale_num, true);
+    if (rc) return rc;
+    const Layout &L = layout_for(scale_num);
+    const int64_t R = rows->n_rows;
+    NetWs w = carve_net(d_ws, ws_bytes, R, train, L.total, L.S);
+    if (!w.ok) {
+        linr_set_error("linr_net_forward: workspace too small (%zu < %zu)", ws_bytes, w.used);
+        return LINR_ENOMEM;
+    }
+    if (R == 0) {
+        if (d_bits) LINR_CHECK_CUDA(cudaMemsetAsync(d_bits, 0, sizeof(double), s));
+        return LINR_OK;
+    }
+    const RowMap m = map_of(rows);
+    {  // SCE
+        SceArgs a = sce_args(d_params, L, rows);
+        a.f0 = T(w.f0, 0, 8);
+        sce_fwd_kernel<<<(unsigned)ceil_div64(R, SCE_TPB), SCE_TPB, 0, s>>>(a);
+    }
+    // GDFE: g = block_in(f0) -> hh[0]
+    BlockBufs bi{w.bi_y, w.bi_t1, w.bi_t0, w.bi_t2, w.bi_z};
+    block_forward(d_params, &L.bin, 1, m, false, nullptr, 0, 0, T(w.f0, 0, 8), bi, T(w.hh, 0, 8), TN(), s);
+    // LDFE_k for k = 0..6, batched (teacher forcing): hh[k+1] = g + block_k(occ[:, :k+1])
+    BlockBufs ob{w.ob_y, w.ob_t1, w.ob_t0, w.ob_t2, w.ob_z};
+    block_forward(d_params, L.ob, 7, m, true, rows->d_occ, 1, 1, TN(), ob, T(w.hh + R * 8, R * 8, 8), T(w.hh, 0, 8), s);
+    // 8 heads
+    const bool want_bits = d_bits != nullptr || train;
+    head_forward(d_params, L, m, 0, 8, T(w.hh, R * 8, 8), train ? w.hc : nullptr, rows->d_occ, d_probs, d_cdf,
+                 train ? w.dzs : nullptr, loss_scale * 1.4426950408889634f, want_bits ? w.bits_partial : nullptr, 0, s);
+    if (d_bits) bits_finalize_kernel<<<1, 256, 0, s>>>(w.bits_partial, (int)ceil_div64(R, CONV_TPB) * 8, d_bits);
+    LINR_LAUNCH_CHECK();
+    return LINR_OK;
+}
+
+int linr_net_backward(const float *d_params, int scale_num, const linr_rows *rows, float *d_grad, void *d_ws,
+                      size_t ws_bytes, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = check_rows(rows, scale_num, true);
+    if (rc) return rc;
+    const Layout &L = layout_for(scale_num);
+    const int64_t R = rows->n_rows;
+    const int P = L.total;
+    NetWs w = carve_net(d_ws, ws_bytes, R, 1, P, L.S);
+    if (!w.ok) {
+        linr_set_error("linr_net_backward: workspace too small (%zu < %zu)", ws_bytes, w.used);
+        return LINR_ENOMEM;
+    }
+    if (R == 0) {
+        LINR_CHECK_CUDA(cudaMemsetAsync(d_grad, 0, sizeof(float) * P, s));
+        return LINR_OK;
+    }
+    const RowMap m = map_of(rows);
+    // heads: dc, MLP weight partials, SConv weight partials, dh_k
+    {
+        HeadBwdArgs a;
+        memset(&a, 0, sizeof(a));
+        a.n_rows = R, a.params = d_params;
+        for (int k = 0; k < 8; ++k) a.w1_off[k] = L.mlp_w1[k], a.b1_off[k] = L.mlp_b1[k], a.w2_off[k] = L.mlp_w2[k], a.b2_off[k] = L.mlp_b2[k];
+        a.c = T(w.hc, R * 8, 8), a.dz = w.dzs, a.dc = T(w.dc, R * 8, 8);
+        a.partial = w.partial, a.P = P, a.chunk = w.chunk;
+        head_bwd_rows_kernel<<<dim3((unsigned)ceil_div64(R, 256), 8), 256, 0, s>>>(a);
+        head_bwd_w_kernel<<<dim3((unsigned)w.n_chunks, 8), 192, 0, s>>>(a);
+    }
+    launch_bwd_w<8, 8, 0>(m, w, P, L.pr_w, L.pr_b, 8, T(w.hh, R * 8, 8), T(w.dc, R * 8, 8), nullptr, 0, 0, s);
+    {
+        ConvArgs a = conv_args(m, d_params);
+        for (int k = 0; k < 8; ++k) a.w_off[k] = L.pr_w[k];
+        a.flip = 1, a.x = T(w.dc, R * 8, 8), a.y = T(w.dhh, R * 8, 8);
+        launch_conv<8, 8, 0>(a, 8, s);
+    }
+    // every h_k contains g: dg = sum_k dh_k
+    sum_groups_kernel<<<(unsigned)ceil_div64(R * 2, 256), 256, 0, s>>>(w.dhh, R * 8, 8, R * 2, w.dg);
+    // LDFE blocks (inputs are occupancy bits: no input gradient)
+    BlockBufs ob{w.ob_y, w.ob_t1, w.ob_t0, w.ob_t2, w.ob_z};
+    BlockGrads gr{w.g_dz, w.g_dt0, w.g_dy, w.g_dt2, w.g_dt1};
+    block_backward(d_params, L.ob, 7, m, w, P, true, rows->d_occ, 1, 1, TN(), ob, gr, T(w.dhh + R * 8, R * 8, 8), TN(), s);
+    // GDFE block
+    BlockBufs bi{w.bi_y, w.bi_t1, w.bi_t0, w.bi_t2, w.bi_z};
+    block_backward(d_params, &L.bin, 1, m, w, P, false, nullptr, 0, 0, T(w.f0, 0, 8), bi, gr, T(w.dg, 0, 8), T(w.df0, 0, 8), s);
+    // SCE
+    SceArgs sa = sce_args(d_params, L, rows);
+    sa.df0 = T(w.df0, 0, 8), sa.chunk = w.chunk;
+    sce_bwd_kernel<<<(unsigned)w.n_chunks, 256, 0, s>>>(sa, w.sce_rec);
+    sce_finalize_kernel<<<(unsigned)L.S, 256, 0, s>>>(sa, w.sce_rec, w.n_chunks, d_grad);
+    const int64_t cnt = P - L.conv_first;
+    finalize_grad_kernel<<<(unsigned)ceil_div64(cnt, 256), 256, 0, s>>>(w.partial, P, w.n_chunks, L.conv_first, cnt, d_grad);
+    LINR_LAUNCH_CHECK();
+    return LINR_OK;
+}
+
+int linr_net_decode_begin(const float *d_params, int scale_num, const linr_rows *rows, void *d_ws, size_t ws_bytes, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = check_rows(rows, scale_num, false);
+    if (rc) return rc;
+    const Layout &L = layout_for(scale_num);
+    const int64_t R = rows->n_rows;
+    NetWs w = carve_net(d_ws, ws_bytes, R, 0, L.total, L.S);
+    if (!w.ok) {
+        linr_set_error("linr_net_decode_begin: workspace too small (%zu < %zu)", ws_bytes, w.used);
+        return LINR_ENOMEM;
+    }
+    if (R == 0) return LINR_OK;
+    const RowMap m = map_of(rows);
+    SceArgs a = sce_args(d_params, L, rows);
+    a.f0 = T(w.f0, 0, 8);
+    sce_fwd_kernel<<<(unsigned)ceil_div64(R, SCE_TPB), SCE_TPB, 0, s>>>(a);
+    BlockBufs bi{w.bi_y, w.bi_t1, w.bi_t0, w.bi_t2, w.bi_z};
+    block_forward(d_params, &L.bin, 1, m, false, nullptr, 0, 0, T(w.f0, 0, 8), bi, T(w.hh, 0, 8), TN(), s);
+    LINR_LAUNCH_CHECK();
+    return LINR_OK;
+}
+
+int linr_net_decode_stage(const float *d_params, int scale_num, const linr_rows *rows, int stage, float *d_probs_stage,
+                          uint16_t *d_cdf_stage, void *d_ws, size_t ws_bytes, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = check_rows(rows, scale_num, true);
+    if (rc) return rc;
+    LINR_REQUIRE(stage >= 0 && stage < 8, "stage out of range");
+    const Layout &L = layout_for(scale_num);
+    const int64_t R = rows->n_rows;
+    NetWs w = carve_net(d_ws, ws_bytes, R, 0, L.total, L.S);
+    if (!w.ok) {
+        linr_set_error("linr_net_decode_stage: workspace too small");
+        return LINR_ENOMEM;
+    }
+    if (R == 0) return LINR_OK;
+    const RowMap m = map_of(rows);
+    Tens h = T(w.hh, 0, 8);
+    if (stage > 0) {
+        // same kernels, same per-row arithmetic as the batched encoder path: one group, cin = stage
+        BlockBufs ob{w.ob_y, w.ob_t1, w.ob_t0, w.ob_t2, w.ob_z};
+        block_forward(d_params, &L.ob[stage - 1], 1, m, true, rows->d_occ, stage, 0, TN(), ob, T(w.hh + R * 8, 0, 8), T(w.hh, 0, 8), s);
+        h = T(w.hh + R * 8, 0, 8);
+    }
+    head_forward(d_params, L, m, stage, 1, h, nullptr, rows->d_occ, d_probs_stage, d_cdf_stage, nullptr, 0.f, nullptr, stage, s);
+    LINR_LAUNCH_CHECK();
+    return LINR_OK;
+}
+
+int linr_occ_set_stage(uint8_t *d_occ, const uint8_t *d_sym, int64_t n_rows, int stage, void *stream) {
+    LINR_REQUIRE(stage >= 0 && stage < 8, "stage out of range");
+    if (n_rows <= 0) return LINR_OK;
+    occ_set_stage_kernel<<<(unsigned)ceil_div64(n_rows, 256), 256, 0, (cudaStream_t)stream>>>(d_occ, d_sym, n_rows, stage);
+    LINR_LAUNCH_CHECK();
+    return LINR_OK;
+}
+
+// ---- single-layer entry points ---------------------------------------------------------------------------
+static int conv_dims_ok(int cin, int cout) { return (cin == 4 || cin == 8) && (cout == 4 || cout == 8); }
+
+static void conv_dispatch(const ConvArgs &a, int cin, int cout, cudaStream_t s) {
+    if (cin == 8 && cout == 8) launch_conv<8, 8, 0>(a, 1, s);
+    else if (cin == 8 && cout == 4) launch_conv<8, 4, 0>(a, 1, s);
+    else if (cin == 4 && cout == 8) launch_conv<4, 8, 0>(a, 1, s);
+    else launch_conv<4, 4, 0>(a, 1, s);
+}
+
+int linr_spconv27_fwd(const float *d_x, int cin, const float *d_w, const float *d_bias, float *d_y, int cout,
+                      const linr_rows *rows, int relu, void *stream) {
+    LINR_REQUIRE(conv_dims_ok(cin, cout), "linr_spconv27_fwd: channels must be 4 or 8 (got %d -> %d)", cin, cout);
+    LINR_REQUIRE(rows && rows->ld >= rows->n_rows, "bad rows");
+    ConvArgs a = conv_args(map_of(rows), d_w);
+    a.w_off[0] = 0;
+    a.bias_direct = d_bias;
+    a.x = T(const_cast<float *>(d_x), 0, cin), a.y = T(d_y, 0, cout), a.relu = relu;
+    conv_dispatch(a, cin, cout, (cudaStream_t)stream);
+    LINR_LAUNCH_CHECK();
+    return LINR_OK;
+}
+
+int linr_spconv27_bwd_in(const float *d_dy, int cin, const float *d_w, float *d_dx, int cout, const linr_rows *rows, void *stream) {
+    LINR_REQUIRE(conv_dims_ok(cin, cout), "linr_spconv27_bwd_in: channels must be 4 or 8");
+    LINR_REQUIRE(rows && rows->ld >= rows->n_rows, "bad rows");
+    ConvArgs a = conv_args(map_of(rows), d_w);
+    a.w_off[0] = 0, a.flip = 1;
+    a.x = T(const_cast<float *>(d_dy), 0, cout), a.y = T(d_dx, 0, cin);
+    conv_dispatch(a, cout, cin, (cudaStream_t)stream);  // this launch maps cout channels -> cin channels
+    LINR_LAUNCH_CHECK();
+    return LINR_OK;
+}
+
+size_t linr_spconv27_bwd_w_ws_bytes(int64_t n_rows, int cin, int cout) {
+    return (size_t)chunks_for(n_rows) * (27 * cin * cout + cout) * sizeof(float) + 256;
+}
+
+int linr_spconv27_bwd_w(const float *d_x, int cin, const float *d_dy, int cout, const linr_rows *rows, float *d_dw,
+                        float *d_dbias, void *d_ws, size_t ws_bytes, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    LINR_REQUIRE(conv_dims_ok(cin, cout) && !(cin == 4 && cout == 8), "linr_spconv27_bwd_w: unsupported channels %d -> %d", cin, cout);
+    LINR_REQUIRE(rows && rows->ld >= rows->n_rows, "bad rows");
+    const int64_t R = rows->n_rows;
+    const int P = 27 * cin * cout + cout;
+    NetWs w;
+    w.n_chunks = chunks_for(R);
+    w.chunk = (ceil_div64(R > 0 ? R : 1, w.n_chunks) + 15) / 16 * 16;
+    LINR_REQUIRE(ws_bytes >= (size_t)w.n_chunks * P * sizeof(float), "linr_spconv27_bwd_w: workspace too small");
+    w.partial = (float *)d_ws;
+    const int wo[1] = {0}, bo[1] = {27 * cin * cout};
+    const RowMap m = map_of(rows);
+    const Tens x = T(const_cast<float *>(d_x), 0, cin), dy = T(const_cast<float *>(d_dy), 0, cout);
+    if (cin == 8 && cout == 8) launch_bwd_w<8, 8, 0>(m, w, P, wo, bo, 1, x, dy, nullptr, 0, 0, s);
+    else if (cin == 8 && cout == 4) launch_bwd_w<8, 4, 0>(m, w, P, wo, bo, 1, x, dy, nullptr, 0, 0, s);
+    else launch_bwd_w<4, 4, 0>(m, w, P, wo, bo, 1, x, dy, nullptr, 0, 0, s);
+    finalize_grad_kernel<<<(unsigned)ceil_div64(27 * cin * cout, 256), 256, 0, s>>>(w.partial, P, w.n_chunks, 0, 27 * cin * cout, d_dw);
+    if (d_dbias) finalize_grad_kernel<<<1, 256, 0, s>>>(w.partial, P, w.n_chunks, 27 * cin * cout, cout, d_dbias - 27 * cin * cout);
+    LINR_LAUNCH_CHECK();
+    return LINR_OK;
+}
+
+int linr_adam_fused(float *d_params, const float *d_grad, float *d_m, float *d_v, int64_t n, int64_t step, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, void *stream) {
+    LINR_REQUIRE(step >= 1, "Adam step is 1-based");
+    if (n <= 0) return LINR_OK;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    adam_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(d_params, d_grad, d_m, d_v, n, lr, beta1, beta2, eps,
+                                                                                 weight_decay, (float)bc1, (float)sqrt(bc2));
+    LINR_LAUNCH_CHECK();
+    return LINR_OK;
+}
+
+int linr_param_quant(const float *d_params, int64_t n, int bitdepth, uint8_t *d_q, float *d_recon, float *d_stats, void *stream) {
+    LINR_REQUIRE(bitdepth >= 1 && bitdepth <= 8, "bitdepth must be in [1,8]");
+    LINR_REQUIRE(n > 0, "empty parameter vector");
+    quant_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_params, n, (float)((1 << bitdepth) - 1), d_q, d_recon, d_stats);
+    LINR_LAUNCH_CHECK();
+    return LINR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,803 @@
+// Device kernels of the occupancy network (fp32, deterministic).  See DESIGN.md "Kernels".
+//
+// Thread mapping (forward / grad-input): ONE THREAD PER OUTPUT ROW; the per-row arithmetic order is
+// fixed (offset column c = 0..8, then dz = -1,0,+1, then input channel) and does not depend on the
+// grid, on grouping or on which stage/scale is being processed -> encoder (batched, teacher forced)
+// and decoder (sequential) produce bit-identical probabilities.
+// Weight gradients: block partial sums in registers, warp-shuffle tree, one partial vector per row
+// chunk, summed later in chunk order (no floating-point atomics anywhere).
+#pragma once
+#include "common.cuh"
+
+namespace linr {
+
+constexpr int MAXG = 8;  // max groups per launch (7 LDFE blocks / 8 heads)
+
+struct Tens {
+    float *p;
+    int64_t gs;  // group stride (floats)
+    int ld;      // row stride (floats)
+    int off;     // first column
+};
+__device__ __forceinline__ float *tptr(const Tens &t, int g, int64_t row) { return t.p + g * t.gs + row * (int64_t)t.ld + t.off; }
+
+struct RowMap {
+    const int32_t *anchor;
+    int64_t ld;
+    const uint32_t *mask;
+    int64_t n_rows;
+};
+
+template <int C>
+__device__ __forceinline__ void load_row(const float *p, float (&v)[C]) {
+    static_assert(C % 4 == 0, "rows are float4 multiples");
+#pragma unroll
+    for (int i = 0; i < C; i += 4) {
+        const float4 q = *reinterpret_cast<const float4 *>(p + i);
+        v[i] = q.x, v[i + 1] = q.y, v[i + 2] = q.z, v[i + 3] = q.w;
+    }
+}
+template <int C>
+__device__ __forceinline__ void store_row(float *p, const float (&v)[C]) {
+#pragma unroll
+    for (int i = 0; i < C; i += 4) *reinterpret_cast<float4 *>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3x3x3 sparse convolution, output-stationary gather.
+//   MODE 0: float input [rows,CIN];  MODE 1: input = low `cin` bits of occ[row] (teacher-forced
+//   sibling occupancy, values {0,1}); MODE 2: float input + fused head (MLP 8->24->1, sigmoid, bits, CDF).
+// ------------------------------------------------------------------------------------------------
+struct ConvArgs {
+    RowMap map;
+    const float *params;
+    int w_off[MAXG], b_off[MAXG];  // per group offsets into params; b_off < 0: no bias
+    const float *bias_direct;      // single-layer API: bias pointer (overrides b_off)
+    int flip;                      // weights are W_f[27][COUT][CIN] of the forward conv; use W'[k][ci][co] = W_f[26-k][co][ci]
+    Tens x;
+    const uint8_t *occ;
+    int cin_base, cin_step;  // MODE 1: cin = cin_base + g * cin_step
+    Tens y, res, rmask;      // res.p / rmask.p may be null
+    int relu, accum;
+    // MODE 2 (head)
+    int w1_off[MAXG], b1_off[MAXG], w2_off[MAXG], b2_off[MAXG];
+    int stage_base;      // group g predicts octant stage_base + g
+    int stage_out_base;  // outputs are written at stage index (stage - stage_out_base)
+    float *probs;         // [8,n_rows] or null
+    uint16_t *cdf;        // [8,n_rows] or null
+    float *dz;            // [8,n_rows] or null (train)
+    float dz_scale;       // loss_scale / ln2
+    float *bits_partial;  // [gridDim.y * gridDim.x] or null
+    int64_t out_ld;       // row count used as the stage stride of probs/cdf/dz
+};
+
+constexpr int CONV_TPB = 128;
+
+template <int CIN, int COUT, int MODE>
+__global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
+    constexpr int WMAX = (MODE == 1) ? 27 * 7 * COUT : 27 * CIN * COUT;
+    __shared__ __align__(16) float s_w[WMAX];
+    __shared__ float s_b[COUT];
+    __shared__ float s_head[(MODE == 2) ? (24 * 8 + 24 + 24 + 1) : 1];
+    __shared__ float s_red[CONV_TPB / 32];
+    const int g = blockIdx.y;
+    const int cin = (MODE == 1) ? (a.cin_base + g * a.cin_step) : CIN;
+    {
+        const float *w = a.params + a.w_off[g];
+        const int n = 27 * cin * COUT;
+        if (!a.flip) {
+            for (int i = threadIdx.x; i < n; i += CONV_TPB) s_w[i] = w[i];
+        } else {
+            // s_w[k][ci][co] = W_f[26-k][co][ci],  W_f is [27][COUT][CIN]
+            for (int i = threadIdx.x; i < n; i += CONV_TPB) {
+                const int k = i / (CIN * COUT), r = i % (CIN * COUT), ci = r / COUT, co = r % COUT;
+                s_w[i] = w[(26 - k) * CIN * COUT + co * CIN + ci];
+            }
+        }
+        if (threadIdx.x < COUT)
+            s_b[threadIdx.x] = a.bias_direct ? a.bias_direct[threadIdx.x] : (a.b_off[g] >= 0 ? a.params[a.b_off[g] + threadIdx.x] : 0.f);
+        if (MODE == 2) {
+            for (int i = threadIdx.x; i < 24 * 8; i += CONV_TPB) s_head[i] = a.params[a.w1_off[g] + i];
+            if (threadIdx.x < 24) {
+                s_head[192 + threadIdx.x] = a.params[a.b1_off[g] + threadIdx.x];
+                s_head[216 + threadIdx.x] = a.params[a.w2_off[g] + threadIdx.x];
+            }
+            if (threadIdx.x == 0) s_head[240] = a.params[a.b2_off[g]];
+        }
+    }
+    __syncthreads();
+    const int64_t row = blockIdx.x * (int64_t)CONV_TPB + threadIdx.x;
+    const bool live = row < a.map.n_rows;
+    float bits = 0.f;
+    if (live) {
+        float acc[COUT];
+#pragma unroll
+        for (int i = 0; i < COUT; ++i) acc[i] = 0.f;
+        const uint32_t m = a.map.mask[row];
+#pragma unroll 1
+        for (int c = 0; c < 9; ++c) {
+            const uint32_t m3 = (m >> (3 * c)) & 7u;
+            if (m3 == 0) continue;
+            int nb = a.map.anchor[c * a.map.ld + row];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                if ((m3 >> j) & 1u) {
+                    const float *wk = s_w + (c + 9 * j) * cin * COUT;
+                    if (MODE == 1) {
+                        const unsigned o = a.occ[nb];
+#pragma unroll
+                        for (int ci = 0; ci < 7; ++ci) {
+                            if (ci < cin && ((o >> ci) & 1u)) {
+#pragma unroll
+                                for (int co = 0; co < COUT; ++co) acc[co] += wk[ci * COUT + co];
+                            }
+                        }
+                    } else {
+                        float xv[CIN];
+                        load_row<CIN>(tptr(a.x, g, nb), xv);
+#pragma unroll
+                        for (int ci = 0; ci < CIN; ++ci) {
+#pragma unroll
+                            for (int co = 0; co < COUT; ++co) acc[co] = fmaf(xv[ci], wk[ci * COUT + co], acc[co]);
+                        }
+                    }
+                    ++nb;
+                }
+            }
+        }
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[co] += s_b[co];
+
+        if (MODE != 2) {
+            if (a.res.p) {
+                float r[COUT];
+                load_row<COUT>(tptr(a.res, g, row), r);
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) acc[co] += r[co];
+            }
+            if (a.accum) {
+                float r[COUT];
+                load_row<COUT>(tptr(a.y, g, row), r);
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) acc[co] += r[co];
+            }
+            if (a.relu) {
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) acc[co] = fmaxf(acc[co], 0.f);
+            }
+            if (a.rmask.p) {
+                float r[COUT];
+                load_row<COUT>(tptr(a.rmask, g, row), r);
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) acc[co] = r[co] > 0.f ? acc[co] : 0.f;
+            }
+            store_row<COUT>(tptr(a.y, g, row), acc);
+        } else {
+            if (a.y.p) store_row<COUT>(tptr(a.y, g, row), acc);
+            // MLP_k 8 -> 24 -> 1 (models/upsample.py:49-55,156-160), fixed order
+            float z = s_head[240];
+#pragma unroll 4
+            for (int j = 0; j < 24; ++j) {
+                float h = s_head[192 + j];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) h = fmaf(s_head[j * 8 + i], acc[i], h);
+                h = fmaxf(h, 0.f);
+                z = fmaf(s_head[216 + j], h, z);
+            }
+            const float p = 1.f / (1.f + expf(-z));
+            const int stage = a.stage_base + g;
+            const int64_t o = (stage - a.stage_out_base) * a.out_ld + row;
+            if (a.probs) a.probs[o] = p;
+            if (a.cdf) a.cdf[o] = (uint16_t)(__float2int_rn(__fmul_rn(__fsub_rn(1.f, p), 65534.f)) + 1);
+            if (a.bits_partial || a.dz) {
+                const float y = (float)((a.occ[row] >> stage) & 1u);
+                const float q = __fsub_rn(1.f, p);
+                // nn.BCELoss clamps log at -100 (models/model_core.py:14)
+                const float lp = fmaxf(logf(p), -100.f), lq = fmaxf(logf(q), -100.f);
+                bits = -(y * lp + (1.f - y) * lq) * 1.4426950408889634f;
+                if (a.dz) {
+                    // BCELoss backward (/max((1-p)p, 1e-12)) followed by sigmoid backward (*p(1-p))
+                    const float pq = q * p;
+                    a.dz[o] = (p - y) / fmaxf(pq, 1e-12f) * pq * a.dz_scale;
+                }
+            }
+        }
+    }
+    if (MODE == 2 && a.bits_partial) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, o);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = bits;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < CONV_TPB / 32; ++w) t += s_red[w];
+            a.bits_partial[blockIdx.y * gridDim.x + blockIdx.x] = t;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient of the 3x3x3 conv: dW[k][ci][co] = sum_o x[nbr(o,k)][ci] * dy[o][co], db = sum_o dy[o].
+// Block = 27 offsets x 8 row-subsets (+8 bias threads); each thread keeps CIN*COUT sums in registers.
+// ------------------------------------------------------------------------------------------------
+struct BwdWArgs {
+    RowMap map;
+    int w_off[MAXG], b_off[MAXG];
+    Tens x, dy;
+    const uint8_t *occ;
+    int cin_base, cin_step;
+    float *partial;  // [n_chunks][P]
+    int64_t P;
+    int64_t chunk;  // rows per chunk (multiple of 8)
+};
+constexpr int BWDW_TPB = 224;
+
+template <int CIN, int COUT, int MODE>
+__global__ void __launch_bounds__(BWDW_TPB) conv27_bwd_w_kernel(const BwdWArgs a) {
+    constexpr int CI = (MODE == 1) ? 7 : CIN;
+    const int g = blockIdx.y;
+    const int cin = (MODE == 1) ? (a.cin_base + g * a.cin_step) : CIN;
+    const int tid = threadIdx.x;
+    const int64_t r0 = blockIdx.x * a.chunk;
+    const int64_t r1 = min(r0 + a.chunk, a.map.n_rows);
+    float *out = a.partial + blockIdx.x * a.P;
+    if (tid < 216) {
+        const int k = tid >> 3, sub = tid & 7;
+        const int c = k % 9, j = k / 9;
+        float acc[CI * COUT];
+#pragma unroll
+        for (int i = 0; i < CI * COUT; ++i) acc[i] = 0.f;
+        for (int64_t r = r0 + sub; r < r1; r += 8) {
+            const uint32_t m3 = (a.map.mask[r] >> (3 * c)) & 7u;
+            if (!((m3 >> j) & 1u)) continue;
+            const int nb = a.map.anchor[c * a.map.ld + r] + __popc(m3 & ((1u << j) - 1u));
+            float dyv[COUT];
+            load_row<COUT>(tptr(a.dy, g, r), dyv);
+            if (MODE == 1) {
+                const unsigned o = a.occ[nb];
+#pragma unroll
+                for (int ci = 0; ci < CI; ++ci) {
+                    const float xb = (ci < cin && ((o >> ci) & 1u)) ? 1.f : 0.f;
+#pragma unroll
+                    for (int co = 0; co < COUT; ++co) acc[ci * COUT + co] = fmaf(xb, dyv[co], acc[ci * COUT + co]);
+                }
+            } else {
+                float xv[CIN];
+                load_row<CIN>(tptr(a.x, g, nb), xv);
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci) {
+#pragma unroll
+                    for (int co = 0; co < COUT; ++co) acc[ci * COUT + co] = fmaf(xv[ci], dyv[co], acc[ci * COUT + co]);
+                }
+            }
+        }
+        // 8 subsets live in 8 adjacent lanes: fixed xor tree.  Warp 6 holds only 24 conv lanes (the
+        // other 8 lanes are the bias threads below), so its shuffle mask is narrower.
+        const unsigned wmask = tid >= 192 ? 0x00ffffffu : 0xffffffffu;
+#pragma unroll
+        for (int i = 0; i < CI * COUT; ++i) {
+            float v = acc[i];
+            v += __shfl_xor_sync(wmask, v, 1);
+            v += __shfl_xor_sync(wmask, v, 2);
+            v += __shfl_xor_sync(wmask, v, 4);
+            acc[i] = v;
+        }
+        if (sub == 0) {
+            float *w = out + a.w_off[g] + k * cin * COUT;
+#pragma unroll
+            for (int ci = 0; ci < CI; ++ci) {
+                if (ci < cin) {
+#pragma unroll
+                    for (int co = 0; co < COUT; ++co) w[ci * COUT + co] = acc[ci * COUT + co];
+                }
+            }
+        }
+    } else {
+        const int sub = tid - 216;
+        float acc[COUT];
+#pragma unroll
+        for (int i = 0; i < COUT; ++i) acc[i] = 0.f;
+        for (int64_t r = r0 + sub; r < r1; r += 8) {
+            float dyv[COUT];
+            load_row<COUT>(tptr(a.dy, g, r), dyv);
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) acc[co] += dyv[co];
+        }
+#pragma unroll
+        for (int i = 0; i < COUT; ++i) {
+            float v = acc[i];
+            v += __shfl_xor_sync(0xff000000u, v, 1);
+            v += __shfl_xor_sync(0xff000000u, v, 2);
+            v += __shfl_xor_sync(0xff000000u, v, 4);
+            acc[i] = v;
+        }
+        if (sub == 0 && a.b_off[g] >= 0) {
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) out[a.b_off[g] + co] = acc[co];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pointwise (kernel_size = 1) convs of the Inception block: y = x @ W[CIN,COUT] + b.
+// ------------------------------------------------------------------------------------------------
+struct PwArgs {
+    int64_t n_rows;
+    const float *params;
+    int w_off[MAXG], b_off[MAXG];
+    int transpose;  // backward: dx[ci] = sum_co dy[co] * W[ci][co]  (template dims are (in,out) of THIS launch)
+    Tens x, y, res, rmask;
+    int relu, accum;
+};
+constexpr int PW_TPB = 256;
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(PW_TPB) pw_kernel(const PwArgs a) {
+    __shared__ float s_w[CIN * COUT];
+    __shared__ float s_b[COUT];
+    const int g = blockIdx.y;
+    if (threadIdx.x < CIN * COUT) {
+        const int i = threadIdx.x, ci = i / COUT, co = i % COUT;
+        // forward: W[ci][co] row-major [CIN][COUT]; transpose: stored W_f[COUT][CIN], want s_w[ci][co] = W_f[co][ci]
+        s_w[i] = a.transpose ? a.params[a.w_off[g] + co * CIN + ci] : a.params[a.w_off[g] + i];
+    }
+    if (threadIdx.x < COUT) s_b[threadIdx.x] = a.b_off[g] >= 0 ? a.params[a.b_off[g] + threadIdx.x] : 0.f;
+    __syncthreads();
+    const int64_t row = blockIdx.x * (int64_t)PW_TPB + threadIdx.x;
+    if (row >= a.n_rows) return;
+    float xv[CIN], acc[COUT];
+    load_row<CIN>(tptr(a.x, g, row), xv);
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[co] = fmaf(xv[ci], s_w[ci * COUT + co], acc[co]);
+    }
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] += s_b[co];
+    if (a.res.p) {
+        float r[COUT];
+        load_row<COUT>(tptr(a.res, g, row), r);
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[co] += r[co];
+    }
+    if (a.accum) {
+        float r[COUT];
+        load_row<COUT>(tptr(a.y, g, row), r);
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[co] += r[co];
+    }
+    if (a.relu) {
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[co] = fmaxf(acc[co], 0.f);
+    }
+    if (a.rmask.p) {
+        float r[COUT];
+        load_row<COUT>(tptr(a.rmask, g, row), r);
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[co] = r[co] > 0.f ? acc[co] : 0.f;
+    }
+    store_row<COUT>(tptr(a.y, g, row), acc);
+}
+
+// dW[ci][co] = sum_r x[r][ci] dy[r][co], db[co] = sum_r dy[r][co]; one partial per row chunk.
+struct PwBwdWArgs {
+    int64_t n_rows;
+    int w_off[MAXG], b_off[MAXG];
+    Tens x, dy;
+    float *partial;
+    int64_t P, chunk;
+};
+constexpr int PWW_TPB = 256;
+
+template <int N>
+__device__ __forceinline__ void block_reduce_store(float (&acc)[N], float *s_red /* [TPB/32][N] */, int tpb) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        float v = acc[i];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        acc[i] = v;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) s_red[warp * N + i] = acc[i];
+    }
+    __syncthreads();
+    (void)tpb;
+}
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(PWW_TPB) pw_bwd_w_kernel(const PwBwdWArgs a) {
+    constexpr int N = CIN * COUT + COUT;
+    __shared__ float s_red[(PWW_TPB / 32) * N];
+    const int g = blockIdx.y;
+    const int64_t r0 = blockIdx.x * a.chunk, r1 = min(r0 + a.chunk, a.n_rows);
+    float acc[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) acc[i] = 0.f;
+    for (int64_t r = r0 + threadIdx.x; r < r1; r += PWW_TPB) {
+        float xv[CIN], dyv[COUT];
+        load_row<CIN>(tptr(a.x, g, r), xv);
+        load_row<COUT>(tptr(a.dy, g, r), dyv);
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) acc[ci * COUT + co] = fmaf(xv[ci], dyv[co], acc[ci * COUT + co]);
+        }
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[CIN * COUT + co] += dyv[co];
+    }
+    block_reduce_store<N>(acc, s_red, PWW_TPB);
+    float *out = a.partial + blockIdx.x * a.P;
+    for (int i = threadIdx.x; i < N; i += PWW_TPB) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < PWW_TPB / 32; ++w) t += s_red[w * N + i];
+        if (i < CIN * COUT) out[a.w_off[g] + i] = t;
+        else out[a.b_off[g] + (i - CIN * COUT)] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Scale-context extraction (models/model_core.py:46-53): f0 = W2_s relu(W1_s [emb_s | nbr7] + b1_s) + b2_s.
+// The embedding part of layer 1 is folded into a per-scale effective bias.
+// ------------------------------------------------------------------------------------------------
+constexpr int MAXS = 12;
+struct SceArgs {
+    int64_t n_rows;
+    int scale_num;
+    const float *params;
+    int emb_off;
+    int w1_off[MAXS], b1_off[MAXS], w2_off[MAXS], b2_off[MAXS];
+    const uint8_t *nbr7, *scale;
+    int scale_fixed;  // >= 0: every row belongs to this scale (decoder path, scale array null)
+    Tens f0;          // fwd out
+    Tens df0;         // bwd in
+    float *partial;
+    int64_t P, chunk;
+};
+constexpr int SCE_TPB = 256;
+constexpr int SCE_SM = 16 + 16 * 7 + 8 * 16 + 8;  // b1eff, W1n[16][7], W2[8][16], b2
+
+__device__ __forceinline__ void sce_stage_scale(const SceArgs &a, int s, float *dst) {
+    // dst: [b1eff 16][W1n 16*7][W2 8*16][b2 8]
+    const float *w1 = a.params + a.w1_off[s];  // [16][15]
+    for (int i = threadIdx.x; i < SCE_SM; i += blockDim.x) {
+        float v;
+        if (i < 16) {
+            v = a.params[a.b1_off[s] + i];
+            for (int e = 0; e < 8; ++e) v = fmaf(w1[i * 15 + e], a.params[a.emb_off + s * 8 + e], v);
+        } else if (i < 16 + 112) {
+            const int j = (i - 16) / 7, b = (i - 16) % 7;
+            v = w1[j * 15 + 8 + b];
+        } else if (i < 16 + 112 + 128) {
+            v = a.params[a.w2_off[s] + (i - 128)];
+        } else {
+            v = a.params[a.b2_off[s] + (i - 256)];
+        }
+        dst[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(SCE_TPB) sce_fwd_kernel(const SceArgs a) {
+    __shared__ float s_p[MAXS * SCE_SM];
+    if (a.scale_fixed >= 0) sce_stage_scale(a, a.scale_fixed, s_p);
+    else
+        for (int s = 0; s < a.scale_num; ++s) sce_stage_scale(a, s, s_p + s * SCE_SM);
+    __syncthreads();
+    const int64_t row = blockIdx.x * (int64_t)SCE_TPB + threadIdx.x;
+    if (row >= a.n_rows) return;
+    const float *p = a.scale_fixed >= 0 ? s_p : s_p + a.scale[row] * SCE_SM;
+    const unsigned bits = a.nbr7[row];
+    float out[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) out[c] = p[256 + c];
+#pragma unroll 4
+    for (int j = 0; j < 16; ++j) {
+        float h = p[j];
+#pragma unroll
+        for (int b = 0; b < 7; ++b)
+            if ((bits >> b) & 1u) h += p[16 + j * 7 + b];
+        h = fmaxf(h, 0.f);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) out[c] = fmaf(p[128 + c * 16 + j], h, out[c]);
+    }
+    store_row<8>(tptr(a.f0, 0, row), out);
+}
+
+// Backward: thread = (hidden unit j, row subset sub of 16); flushes per scale segment inside its chunk.
+// Per (chunk, scale) it writes: dW2[:, j] (8), dW1n[j][0..6], db1eff[j]; threads j<8 also db2[j].
+// Layout of one SCE partial record per scale (floats): [dW2 8*16][db2 8][dW1n 16*7][db1eff 16] = 264
+constexpr int SCE_REC = 128 + 8 + 112 + 16;
+__global__ void __launch_bounds__(256) sce_bwd_kernel(const SceArgs a, float *rec /* [n_chunks][scale_num][SCE_REC] */) {
+    __shared__ float s_p[MAXS * SCE_SM];
+    for (int s = 0; s < a.scale_num; ++s) sce_stage_scale(a, s, s_p + s * SCE_SM);
+    __syncthreads();
+    const int j = threadIdx.x >> 4, sub = threadIdx.x & 15;
+    const int64_t r0 = blockIdx.x * a.chunk, r1 = min(r0 + a.chunk, a.n_rows);
+    float *out = rec + (int64_t)blockIdx.x * a.scale_num * SCE_REC;
+    for (int s = 0; s < a.scale_num; ++s) {
+        const float *p = s_p + s * SCE_SM;
+        float aw2[8], aw1[7], ab1 = 0.f, ab2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) aw2[c] = 0.f;
+#pragma unroll
+        for (int b = 0; b < 7; ++b) aw1[b] = 0.f;
+        for (int64_t r = r0 + sub; r < r1; r += 16) {
+            const int rs = a.scale_fixed >= 0 ? a.scale_fixed : a.scale[r];
+            if (rs != s) continue;
+            const unsigned bits = a.nbr7[r];
+            float d[8];
+            load_row<8>(tptr(a.df0, 0, r), d);
+            float h = p[j];
+#pragma unroll
+            for (int b = 0; b < 7; ++b)
+                if ((bits >> b) & 1u) h += p[16 + j * 7 + b];
+            h = fmaxf(h, 0.f);
+            float dh = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                aw2[c] = fmaf(d[c], h, aw2[c]);
+                dh = fmaf(p[128 + c * 16 + j], d[c], dh);
+            }
+            dh = h > 0.f ? dh : 0.f;
+#pragma unroll
+            for (int b = 0; b < 7; ++b)
+                if ((bits >> b) & 1u) aw1[b] += dh;
+            ab1 += dh;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) ab2 += (c == j) ? d[c] : 0.f;
+        }
+        // reduce over the 16 subsets (16 adjacent lanes)
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) aw2[c] += __shfl_xor_sync(0xffffffffu, aw2[c], o);
+#pragma unroll
+            for (int b = 0; b < 7; ++b) aw1[b] += __shfl_xor_sync(0xffffffffu, aw1[b], o);
+            ab1 += __shfl_xor_sync(0xffffffffu, ab1, o);
+            ab2 += __shfl_xor_sync(0xffffffffu, ab2, o);
+        }
+        if (sub == 0) {
+            float *o = out + s * SCE_REC;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) o[c * 16 + j] = aw2[c];
+            if (j < 8) o[128 + j] = ab2;
+#pragma unroll
+            for (int b = 0; b < 7; ++b) o[136 + j * 7 + b] = aw1[b];
+            o[248 + j] = ab1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Head backward.  rows kernel: dc[k][row][8] = W1^T (dz * w2 * [hidden>0]);  weights kernel: (j, sub) mapping.
+// ------------------------------------------------------------------------------------------------
+struct HeadBwdArgs {
+    int64_t n_rows;
+    const float *params;
+    int w1_off[MAXG], b1_off[MAXG], w2_off[MAXG], b2_off[MAXG];
+    Tens c;           // saved conv outputs [8][rows][8]
+    const float *dz;  // [8][rows]
+    Tens dc;          // out
+    float *partial;
+    int64_t P, chunk;
+};
+
+__global__ void __launch_bounds__(256) head_bwd_rows_kernel(const HeadBwdArgs a) {
+    __shared__ float s_head[241];
+    const int g = blockIdx.y;
+    for (int i = threadIdx.x; i < 192; i += 256) s_head[i] = a.params[a.w1_off[g] + i];
+    if (threadIdx.x < 24) {
+        s_head[192 + threadIdx.x] = a.params[a.b1_off[g] + threadIdx.x];
+        s_head[216 + threadIdx.x] = a.params[a.w2_off[g] + threadIdx.x];
+    }
+    __syncthreads();
+    const int64_t row = blockIdx.x * 256ll + threadIdx.x;
+    if (row >= a.n_rows) return;
+    float c[8], dc[8];
+    load_row<8>(tptr(a.c, g, row), c);
+    const float dz = a.dz[g * a.n_rows + row];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dc[i] = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < 24; ++j) {
+        float h = s_head[192 + j];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h = fmaf(s_head[j * 8 + i], c[i], h);
+        const float dh = h > 0.f ? dz * s_head[216 + j] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dc[i] = fmaf(s_head[j * 8 + i], dh, dc[i]);
+    }
+    store_row<8>(tptr(a.dc, g, row), dc);
+}
+
+// block 192 threads: j = tid>>3 (24 hidden units), sub = tid&7
+__global__ void __launch_bounds__(192) head_bwd_w_kernel(const HeadBwdArgs a) {
+    const int g = blockIdx.y;
+    const int j = threadIdx.x >> 3, sub = threadIdx.x & 7;
+    const int64_t r0 = blockIdx.x * a.chunk, r1 = min(r0 + a.chunk, a.n_rows);
+    float w1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w1[i] = a.params[a.w1_off[g] + j * 8 + i];
+    const float b1 = a.params[a.b1_off[g] + j], w2 = a.params[a.w2_off[g] + j];
+    float aw1[8], ab1 = 0.f, aw2 = 0.f, ab2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) aw1[i] = 0.f;
+    for (int64_t r = r0 + sub; r < r1; r += 8) {
+        float c[8];
+        load_row<8>(tptr(a.c, g, r), c);
+        const float dz = a.dz[g * a.n_rows + r];
+        float h = b1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h = fmaf(w1[i], c[i], h);
+        h = fmaxf(h, 0.f);
+        const float dh = h > 0.f ? dz * w2 : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) aw1[i] = fmaf(dh, c[i], aw1[i]);
+        ab1 += dh;
+        aw2 = fmaf(dz, h, aw2);
+        ab2 += dz;
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) aw1[i] += __shfl_xor_sync(0xffffffffu, aw1[i], o);
+        ab1 += __shfl_xor_sync(0xffffffffu, ab1, o);
+        aw2 += __shfl_xor_sync(0xffffffffu, aw2, o);
+        ab2 += __shfl_xor_sync(0xffffffffu, ab2, o);
+    }
+    if (sub == 0) {
+        float *out = a.partial + blockIdx.x * a.P;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[a.w1_off[g] + j * 8 + i] = aw1[i];
+        out[a.b1_off[g] + j] = ab1;
+        out[a.w2_off[g] + j] = aw2;
+        if (j == 0) out[a.b2_off[g]] = ab2;
+    }
+}
+
+// dg[row][8] = sum over the 8 stages of dh_k[row][8] (h_k = g + LDFE_{k-1}: every stage feeds g), fixed order.
+__global__ void sum_groups_kernel(const float *__restrict__ src, int64_t gs, int groups, int64_t n4, float *__restrict__ dst) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 s = reinterpret_cast<const float4 *>(src)[i];
+    for (int g = 1; g < groups; ++g) {
+        const float4 v = reinterpret_cast<const float4 *>(src + g * gs)[i];
+        s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
+    }
+    reinterpret_cast<float4 *>(dst)[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Final reductions, Adam, quantisation
+// ------------------------------------------------------------------------------------------------
+// grad[j] = sum over chunks (in chunk order) of partial[chunk][j] for the conv / MLP parameters.
+__global__ void finalize_grad_kernel(const float *__restrict__ partial, int64_t P, int n_chunks, int64_t first, int64_t count,
+                                     float *__restrict__ grad) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int64_t j = first + i;
+    float t = 0.f;
+    for (int c = 0; c < n_chunks; ++c) t += partial[c * P + j];
+    grad[j] = t;
+}
+
+// SCE: reduce records over chunks, then expand the folded embedding terms (one block per scale).
+__global__ void __launch_bounds__(256) sce_finalize_kernel(const SceArgs a, const float *__restrict__ rec, int n_chunks,
+                                                           float *__restrict__ grad) {
+    __shared__ float s_r[SCE_REC];
+    const int s = blockIdx.x;
+    for (int i = threadIdx.x; i < SCE_REC; i += blockDim.x) {
+        float t = 0.f;
+        for (int c = 0; c < n_chunks; ++c) t += rec[((int64_t)c * a.scale_num + s) * SCE_REC + i];
+        s_r[i] = t;
+    }
+    __syncthreads();
+    const float *emb = a.params + a.emb_off + s * 8;
+    const float *w1 = a.params + a.w1_off[s];
+    for (int i = threadIdx.x; i < 16 * 15; i += blockDim.x) {
+        const int j = i / 15, e = i % 15;
+        grad[a.w1_off[s] + i] = e < 8 ? s_r[248 + j] * emb[e] : s_r[136 + j * 7 + (e - 8)];
+    }
+    for (int i = threadIdx.x; i < 16; i += blockDim.x) grad[a.b1_off[s] + i] = s_r[248 + i];
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) grad[a.w2_off[s] + i] = s_r[i];
+    for (int i = threadIdx.x; i < 8; i += blockDim.x) {
+        grad[a.b2_off[s] + i] = s_r[128 + i];
+        float t = 0.f;
+        for (int j = 0; j < 16; ++j) t = fmaf(w1[j * 15 + i], s_r[248 + j], t);
+        grad[a.emb_off + s * 8 + i] = t;
+    }
+}
+
+__global__ void bits_finalize_kernel(const float *__restrict__ partial, int n, double *__restrict__ out) {
+    // single thread-block, fixed order, double accumulation
+    __shared__ double s[256];
+    double t = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) t += (double)partial[i];
+    s[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = s[0];
+}
+
+// torch.optim.Adam, weight decay added to the gradient (main.py:231-237). bc1/bc2: bias corrections.
+__global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
+                            int64_t n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float pi = p[i];
+    const float gi = fmaf(wd, pi, g[i]);
+    const float mi = fmaf(1.f - b1, gi, b1 * m[i]);
+    const float vi = fmaf((1.f - b2) * gi, gi, b2 * v[i]);
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+}
+
+// One block: min/max -> quantise -> mean -> mean abs dev -> dequantise (model_size_est.py:72-91,410-411).
+__global__ void __launch_bounds__(1024) quant_kernel(const float *__restrict__ p, int64_t n, float smax, uint8_t *__restrict__ q,
+                                                     float *__restrict__ recon, float *__restrict__ stats) {
+    __shared__ float s_a[1024], s_b[1024];
+    __shared__ double s_d[1024];
+    float mn = INFINITY, mx = -INFINITY;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) {
+        mn = fminf(mn, p[i]);
+        mx = fmaxf(mx, p[i]);
+    }
+    s_a[threadIdx.x] = mn, s_b[threadIdx.x] = mx;
+    __syncthreads();
+    for (int o = 512; o; o >>= 1) {
+        if (threadIdx.x < o) {
+            s_a[threadIdx.x] = fminf(s_a[threadIdx.x], s_a[threadIdx.x + o]);
+            s_b[threadIdx.x] = fmaxf(s_b[threadIdx.x], s_b[threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    mn = s_a[0], mx = s_b[0];
+    const float rng = mx - mn;
+    double sum = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) {
+        // round((w - min) / range * smax): same op order as torch (division, then multiply), half-to-even
+        const float s = rintf(__fmul_rn(__fdiv_rn(__fsub_rn(p[i], mn), rng), smax));
+        q[i] = (uint8_t)s;
+        recon[i] = __fadd_rn(__fmul_rn(__fdiv_rn(s, smax), rng), mn);
+        sum += (double)s;
+    }
+    __syncthreads();
+    s_d[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 512; o; o >>= 1) {
+        if (threadIdx.x < o) s_d[threadIdx.x] += s_d[threadIdx.x + o];
+        __syncthreads();
+    }
+    const float mu = rintf((float)(s_d[0] / (double)n));
+    __syncthreads();
+    double dev = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) dev += fabs((double)q[i] - (double)mu);
+    s_d[threadIdx.x] = dev;
+    __syncthreads();
+    for (int o = 512; o; o >>= 1) {
+        if (threadIdx.x < o) s_d[threadIdx.x] += s_d[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        stats[0] = mn, stats[1] = mx, stats[2] = mu;
+        stats[3] = rintf((float)(s_d[0] / (double)n));
+    }
+}
+
+__global__ void occ_set_stage_kernel(uint8_t *__restrict__ occ, const uint8_t *__restrict__ sym, int64_t n, int stage) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) occ[i] = (uint8_t)(occ[i] | ((sym[i] & 1u) << stage));
+}
+
+}  // namespace linr

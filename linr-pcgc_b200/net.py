@@ -1,0 +1,109 @@
+"""Thin host wrapper over the network entry points of the C ABI (forward / backward / decode / Adam / quant).
+
+One `NetRunner` owns the caller-side memory the ABI asks for (workspace, probability / CDF / bit-count
+buffers) for up to `max_rows` rows, so a training loop makes no allocation per iteration.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+from .frame import RowTables
+
+
+def param_count(scale_num: int) -> int:
+    return int(_lib.load().linr_param_count(scale_num))
+
+
+def param_offsets(scale_num: int):
+    buf = (C.c_int64 * 512)()
+    n = _lib.load().linr_param_offsets(scale_num, buf, 512)
+    return [int(buf[i]) for i in range(n)]
+
+
+class NetRunner:
+    def __init__(self, scale_num: int, max_rows: int, device, train: bool = True):
+        self.lib = _lib.load()
+        self.S = scale_num
+        self.P = param_count(scale_num)
+        self.device = torch.device(device)
+        self.train = train
+        self.max_rows = 0
+        self.ws = None
+        self.reserve(max_rows)
+        self.bits = torch.zeros(1, dtype=torch.float64, device=self.device)
+
+    def reserve(self, rows: int):
+        if rows <= self.max_rows and self.ws is not None:
+            return
+        self.max_rows = max(rows, 1)
+        nbytes = self.lib.linr_net_ws_bytes(self.max_rows, 1 if self.train else 0)
+        self.ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        self.probs = torch.empty(8 * self.max_rows, dtype=torch.float32, device=self.device)
+        self.cdf = torch.empty(8 * self.max_rows, dtype=torch.int16, device=self.device)
+
+    # -- teacher-forced forward over all 8 stages ---------------------------------------------------------
+    def forward(self, params: torch.Tensor, t: RowTables, train: bool = False, loss_scale: float = 0.0,
+                want_probs: bool = False, want_cdf: bool = False, want_bits: bool = True):
+        assert params.is_cuda and params.dtype == torch.float32 and params.numel() == self.P
+        assert t.occ is not None, "teacher-forced forward needs the ground-truth occupancy"
+        assert not train or self.train, "runner was created without training workspace"
+        n = t.n_rows
+        self.reserve(n)
+        rows = t.rows()
+        check(self.lib.linr_net_forward(ptr(params), self.S, C.byref(rows), 1 if train else 0, loss_scale,
+                                        ptr(self.probs) if want_probs else None, ptr(self.cdf) if want_cdf else None,
+                                        ptr(self.bits) if want_bits else None, ptr(self.ws), self.ws.numel(), stream_ptr()),
+              "linr_net_forward")
+        out = {}
+        if want_bits:
+            out["bits"] = self.bits
+        if want_probs:
+            out["probs"] = self.probs[: 8 * n].view(8, n)
+        if want_cdf:
+            out["cdf"] = self.cdf[: 8 * n].view(8, n)
+        return out
+
+    def backward(self, params: torch.Tensor, t: RowTables, grad: torch.Tensor):
+        assert grad.is_cuda and grad.numel() == self.P
+        rows = t.rows()
+        check(self.lib.linr_net_backward(ptr(params), self.S, C.byref(rows), ptr(grad), ptr(self.ws), self.ws.numel(),
+                                         stream_ptr()), "linr_net_backward")
+
+    # -- sequential decode ----------------------------------------------------------------------------------
+    def decode_begin(self, params: torch.Tensor, t: RowTables):
+        self.reserve(t.n_rows)
+        rows = t.rows()
+        check(self.lib.linr_net_decode_begin(ptr(params), self.S, C.byref(rows), ptr(self.ws), self.ws.numel(), stream_ptr()),
+              "linr_net_decode_begin")
+
+    def decode_stage(self, params: torch.Tensor, t: RowTables, stage: int, want_probs: bool = False):
+        n = t.n_rows
+        rows = t.rows()
+        check(self.lib.linr_net_decode_stage(ptr(params), self.S, C.byref(rows), stage,
+                                             ptr(self.probs) if want_probs else None, ptr(self.cdf), ptr(self.ws),
+                                             self.ws.numel(), stream_ptr()), "linr_net_decode_stage")
+        return self.cdf[:n], (self.probs[:n] if want_probs else None)
+
+    def occ_set_stage(self, occ: torch.Tensor, sym: torch.Tensor, stage: int):
+        check(self.lib.linr_occ_set_stage(ptr(occ), ptr(sym), int(occ.numel()), stage, stream_ptr()), "linr_occ_set_stage")
+
+
+def adam_step(params, grad, m, v, step: int, lr: float, b1=0.9, b2=0.999, eps=1e-8, wd=1e-4):
+    """torch.optim.Adam with L2 decay (main.py:231-237) on the flat buffers, one launch."""
+    check(_lib.load().linr_adam_fused(ptr(params), ptr(grad), ptr(m), ptr(v), params.numel(), step, lr, b1, b2, eps, wd,
+                                      stream_ptr()), "linr_adam_fused")
+
+
+def param_quant(params: torch.Tensor, bitdepth: int = 8):
+    """quant_uniform2 + Laplace stats (model_size_est.py:72-91,410-411) -> (q u8, recon f32, stats[min,max,mu,b])."""
+    q = torch.empty(params.numel(), dtype=torch.uint8, device=params.device)
+    recon = torch.empty_like(params)
+    stats = torch.empty(4, dtype=torch.float32, device=params.device)
+    check(_lib.load().linr_param_quant(ptr(params), params.numel(), bitdepth, ptr(q), ptr(recon), ptr(stats), stream_ptr()),
+          "linr_param_quant")
+    return q, recon, stats
