@@ -38,6 +38,18 @@ const char *linr_last_error(void);
 /* device properties the host side needs for grid sizing (SM count, L2 bytes). Synchronous. */
 int linr_device_info(int device, int *sm_count, int64_t *l2_bytes);
 
+/* Launch accounting / live kernel timing (no reference counterpart: the reference has no profiler hooks,
+ * SURVEY.md section 5).  Kernel classes are the K_* values of csrc/prof.cuh; linr_prof_name() names them.
+ *  linr_prof_enable(mask): bit c set -> launches of class c are bracketed by CUDA events on their stream
+ *                          (mask 0 disables).  Resets all counters.
+ *  linr_prof_read(c, ...): synchronises the recorded events of class c; total milliseconds, launches and the
+ *                          "units" (rows x groups) those launches processed.  Launch counts are kept for
+ *                          every class even when its timing is disabled. */
+int linr_prof_enable(uint32_t class_mask);
+int linr_prof_read(int cls, double *ms_total, int64_t *launches, int64_t *units);
+int linr_prof_classes(void);
+const char *linr_prof_name(int cls);
+
 /* ------------------------------------------------------------------------------------------------
  * Coordinate stage (integer, bit-exact).  Replaces torch.unique/sort/searchsorted chains.
  * ---------------------------------------------------------------------------------------------- */
@@ -174,10 +186,12 @@ int linr_param_quant(const float *d_params, int64_t n, int bitdepth, uint8_t *d_
  * or -(needed) if cap is too small. */
 int64_t linr_rc_encode_binary(const uint16_t *h_cdf_mid, const uint8_t *h_sym, int64_t n, uint8_t *h_out, int64_t cap);
 int linr_rc_decode_binary(const uint16_t *h_cdf_mid, const uint8_t *h_in, int64_t nbytes, uint8_t *h_sym, int64_t n);
-/* Many independent binary streams at once on `threads` host threads (the 8 stages x S scales of a frame). */
+/* Many independent binary streams at once on `threads` host threads (the 8 stages x S scales of a frame,
+ * models/upsample.py:219-246).  Stream i codes bit h_shift[i] of each byte of h_sym[i] (h_shift NULL: bit 0), so
+ * the 8 stage streams of a scale read the packed occupancy bytes in place.  h_written[i] = bytes, or -(needed). */
 int linr_rc_encode_binary_batch(int n_streams, const uint16_t *const *h_cdf_mid, const uint8_t *const *h_sym,
-                                const int64_t *n, uint8_t *const *h_out, const int64_t *cap, int64_t *h_written,
-                                int threads);
+                                const int *h_shift, const int64_t *n, uint8_t *const *h_out, const int64_t *cap,
+                                int64_t *h_written, int threads);
 /* General alphabet with one shared CDF row of Lp uint16 entries (model.bin Laplace coder). */
 int64_t linr_rc_encode_shared(const uint16_t *h_cdf_row, int Lp, const int16_t *h_sym, int64_t n, uint8_t *h_out,
                               int64_t cap);

@@ -30,6 +30,10 @@ SIGNATURES = {
     "linr_version": (_I, []),
     "linr_last_error": (C.c_char_p, []),
     "linr_device_info": (_I, [_I, C.POINTER(_I), C.POINTER(_I64)]),
+    "linr_prof_enable": (_I, [C.c_uint32]),
+    "linr_prof_read": (_I, [_I, C.POINTER(C.c_double), C.POINTER(_I64), C.POINTER(_I64)]),
+    "linr_prof_classes": (_I, []),
+    "linr_prof_name": (C.c_char_p, [_I]),
     "linr_coord_ws_bytes": (_SZ, [_I64]),
     "linr_coord_sort_unique": (_I, [_P, _I64, _I, _P, _P, _P, _SZ, _P]),
     "linr_coord_sort": (_I, [_P, _I64, _I, _P, _P, _SZ, _P]),
@@ -57,7 +61,7 @@ SIGNATURES = {
     "linr_param_quant": (_I, [_P, _I64, _I, _P, _P, _P, _P]),
     "linr_rc_encode_binary": (_I64, [_P, _P, _I64, _P, _I64]),
     "linr_rc_decode_binary": (_I, [_P, _P, _I64, _P, _I64]),
-    "linr_rc_encode_binary_batch": (_I, [_I, _P, _P, _P, _P, _P, _P, _I]),
+    "linr_rc_encode_binary_batch": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _I]),
     "linr_rc_encode_shared": (_I64, [_P, _I, _P, _I64, _P, _I64]),
     "linr_rc_decode_shared": (_I, [_P, _I, _P, _I64, _P, _I64]),
 }

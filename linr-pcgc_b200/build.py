@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "liblinr_b200.so")
 SOURCES = ["coords.cu", "net.cu", "rc_host.cpp"]
-HEADERS = ["common.cuh", "net_kernels.cuh", os.path.join("..", "..", "include", "linr_b200.h")]
+HEADERS = ["common.cuh", "net_kernels.cuh", "prof.cuh", os.path.join("..", "..", "include", "linr_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
          "-Xcompiler", "-fPIC,-O3,-pthread", "-shared", "-Xptxas", "-warn-spills"]

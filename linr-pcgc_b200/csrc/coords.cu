@@ -4,6 +4,10 @@
 #include <cub/cub.cuh>
 
 #include "common.cuh"
+#include "prof.cuh"
+
+using linr::K_COORD;
+using linr::ProfScope;
 
 namespace {
 
@@ -242,10 +246,19 @@ size_t linr_coord_ws_bytes(int64_t n) {
 int linr_coord_min_sub(const int32_t *d_in, int64_t n, int32_t *d_out, int32_t *d_min, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     LINR_REQUIRE(n > 0, "linr_coord_min_sub: empty input");
-    fill3_kernel<<<1, 32, 0, s>>>(d_min, INT32_MAX);
+    {
+        ProfScope prof(K_COORD, 1, s);
+        fill3_kernel<<<1, 32, 0, s>>>(d_min, INT32_MAX);
+    }
     int g = (int)(ceil_div64(n, TPB) < 1024 ? ceil_div64(n, TPB) : 1024);
-    min3_kernel<<<g, TPB, 0, s>>>(d_in, n, d_min);
-    sub3_kernel<<<grid_for(3 * n), TPB, 0, s>>>(d_in, n, d_min, d_out);
+    {
+        ProfScope prof(K_COORD, 1, s);
+        min3_kernel<<<g, TPB, 0, s>>>(d_in, n, d_min);
+    }
+    {
+        ProfScope prof(K_COORD, 1, s);
+        sub3_kernel<<<grid_for(3 * n), TPB, 0, s>>>(d_in, n, d_min, d_out);
+    }
     LINR_LAUNCH_CHECK();
     return LINR_OK;
 }
@@ -263,7 +276,10 @@ static int sort_impl(const int32_t *d_in, int64_t n, int bits, int shift, bool u
         if (d_n_out) LINR_CHECK_CUDA(cudaMemsetAsync(d_n_out, 0, sizeof(int64_t), s));
         return LINR_OK;
     }
-    pack_kernel<<<grid_for(n), TPB, 0, s>>>(d_in, n, bits, shift, w.a);
+    {
+        ProfScope prof(K_COORD, 1, s);
+        pack_kernel<<<grid_for(n), TPB, 0, s>>>(d_in, n, bits, shift, w.a);
+    }
     size_t cb = w.cub_bytes;
     LINR_CHECK_CUDA(cub::DeviceRadixSort::SortKeys(w.cub, cb, w.a, w.b, (int)n, 0, 3 * bits, s));
     uint64_t *res = w.b;
@@ -272,7 +288,10 @@ static int sort_impl(const int32_t *d_in, int64_t n, int bits, int shift, bool u
         LINR_CHECK_CUDA(cub::DeviceSelect::Unique(w.cub, cb, w.b, w.a, d_n_out, (int)n, s));
         res = w.a;
     }
-    if (d_out) unpack_kernel<<<grid_for(n), TPB, 0, s>>>(res, uniq ? d_n_out : nullptr, n, bits, d_out);
+    if (d_out) {
+        ProfScope prof(K_COORD, 1, s);
+        unpack_kernel<<<grid_for(n), TPB, 0, s>>>(res, uniq ? d_n_out : nullptr, n, bits, d_out);
+    }
     if (keys_out) *keys_out = res;
     LINR_LAUNCH_CHECK();
     return LINR_OK;
@@ -295,7 +314,10 @@ int linr_octree_down(const int32_t *d_child, int64_t nc, int bits, int32_t *d_pa
     int rc = sort_impl(d_child, nc, bits, 1, true, d_parent, d_np, &pkeys, d_ws, ws_bytes, s);
     if (rc) return rc;
     LINR_CHECK_CUDA(cudaMemsetAsync(d_occ, 0, align_up((size_t)nc, 4), s));
-    occ_kernel<<<grid_for(nc), TPB, 0, s>>>(d_child, nc, bits, pkeys, d_np, (uint32_t *)d_occ);
+    {
+        ProfScope prof(K_COORD, 1, s);
+        occ_kernel<<<grid_for(nc), TPB, 0, s>>>(d_child, nc, bits, pkeys, d_np, (uint32_t *)d_occ);
+    }
     LINR_LAUNCH_CHECK();
     return LINR_OK;
 }
@@ -309,7 +331,10 @@ int linr_octree_up_count(const uint8_t *d_occ, int64_t n, int64_t *d_off, void *
         return LINR_ENOMEM;
     }
     int64_t *cnt = (int64_t *)w.a;
-    popc_kernel<<<grid_for(n + 1), TPB, 0, s>>>(d_occ, n, cnt);
+    {
+        ProfScope prof(K_COORD, 1, s);
+        popc_kernel<<<grid_for(n + 1), TPB, 0, s>>>(d_occ, n, cnt);
+    }
     size_t cb = w.cub_bytes;
     LINR_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(w.cub, cb, cnt, d_off, (int)(n + 1), s));
     LINR_LAUNCH_CHECK();
@@ -327,10 +352,16 @@ int linr_octree_up_expand(const int32_t *d_parent, const uint8_t *d_occ, const i
         linr_set_error("workspace too small: have %zu need %zu", ws_bytes, linr_coord_ws_bytes(n_child));
         return LINR_ENOMEM;
     }
-    expand_kernel<<<grid_for(n), TPB, 0, s>>>(d_parent, d_occ, d_off, n, bits, w.a);
+    {
+        ProfScope prof(K_COORD, 1, s);
+        expand_kernel<<<grid_for(n), TPB, 0, s>>>(d_parent, d_occ, d_off, n, bits, w.a);
+    }
     size_t cb = w.cub_bytes;
     LINR_CHECK_CUDA(cub::DeviceRadixSort::SortKeys(w.cub, cb, w.a, w.b, (int)n_child, 0, 3 * bits, s));
-    unpack_kernel<<<grid_for(n_child), TPB, 0, s>>>(w.b, nullptr, n_child, bits, d_child);
+    {
+        ProfScope prof(K_COORD, 1, s);
+        unpack_kernel<<<grid_for(n_child), TPB, 0, s>>>(w.b, nullptr, n_child, bits, d_child);
+    }
     LINR_LAUNCH_CHECK();
     return LINR_OK;
 }
@@ -340,8 +371,14 @@ size_t linr_hash_bytes(int64_t cap) { return (size_t)cap * sizeof(HashSlot); }
 int linr_hash_build(const int32_t *d_xyz, const uint8_t *d_scale, int64_t n, void *d_table, int64_t cap, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     LINR_REQUIRE(cap >= 2 * n && (cap & (cap - 1)) == 0, "hash capacity must be a power of two >= 2n");
-    hash_clear_kernel<<<grid_for(cap), TPB, 0, s>>>((HashSlot *)d_table, cap);
-    if (n > 0) hash_insert_kernel<<<grid_for(n), TPB, 0, s>>>(d_xyz, d_scale, n, (HashSlot *)d_table, cap);
+    {
+        ProfScope prof(K_COORD, 1, s);
+        hash_clear_kernel<<<grid_for(cap), TPB, 0, s>>>((HashSlot *)d_table, cap);
+    }
+    if (n > 0) {
+        ProfScope prof(K_COORD, 1, s);
+        hash_insert_kernel<<<grid_for(n), TPB, 0, s>>>(d_xyz, d_scale, n, (HashSlot *)d_table, cap);
+    }
     LINR_LAUNCH_CHECK();
     return LINR_OK;
 }
@@ -351,8 +388,11 @@ int linr_nbr_build(const int32_t *d_xyz, const uint8_t *d_scale, int64_t n, cons
     cudaStream_t s = (cudaStream_t)stream;
     LINR_REQUIRE(!d_anchor || ld >= n, "anchor leading dimension smaller than n");
     if (n == 0) return LINR_OK;
-    nbr_kernel<<<(int)ceil_div64(n, 128), 128, 0, s>>>(d_xyz, d_scale, n, (const HashSlot *)d_table, cap, d_nbr27, d_anchor,
-                                                        ld, d_mask, d_nbr7);
+    {
+        ProfScope prof(K_COORD, 1, s);
+        nbr_kernel<<<(int)ceil_div64(n, 128), 128, 0, s>>>(d_xyz, d_scale, n, (const HashSlot *)d_table, cap, d_nbr27, d_anchor,
+                                                            ld, d_mask, d_nbr7);
+    }
     LINR_LAUNCH_CHECK();
     return LINR_OK;
 }
@@ -361,7 +401,10 @@ int linr_hash_lookup(const int32_t *d_q, const uint8_t *d_qs, int64_t nq, const 
                      int32_t *d_rows, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (nq == 0) return LINR_OK;
-    hash_lookup_kernel<<<grid_for(nq), TPB, 0, s>>>(d_q, d_qs, nq, (const HashSlot *)d_table, cap, d_rows);
+    {
+        ProfScope prof(K_COORD, 1, s);
+        hash_lookup_kernel<<<grid_for(nq), TPB, 0, s>>>(d_q, d_qs, nq, (const HashSlot *)d_table, cap, d_rows);
+    }
     LINR_LAUNCH_CHECK();
     return LINR_OK;
 }

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "net_kernels.cuh"
+#include "prof.cuh"
 
 using namespace linr;
 
@@ -28,6 +29,61 @@ int linr_sm_count() {
     }
     return sm;
 }
+
+// ---------------------------------------------------------------------------------------------- profiler
+namespace linr {
+namespace {
+struct ProfState {
+    uint32_t mask = 0;
+    int64_t launches[K_NCLASS] = {0};
+    int64_t units[K_NCLASS] = {0};
+    std::vector<cudaEvent_t> ev[K_NCLASS];  // begin/end pairs recorded so far
+    std::vector<cudaEvent_t> pool;          // recycled events
+    double ms_done[K_NCLASS] = {0};
+} g_prof;
+const char *const kNames[K_NCLASS] = {"conv27<8,8>", "conv27<8,4>", "conv27<4,8>", "conv27<4,4>", "conv27_bits<8>", "conv27_head",
+                                      "bwd_w<8,8>", "bwd_w<8,4>", "bwd_w<4,4>", "bwd_w_bits<8>", "pointwise", "pointwise_bwd_w",
+                                      "head_bwd", "sce", "reduce", "adam_quant", "coord"};
+cudaEvent_t prof_event() {
+    if (!g_prof.pool.empty()) {
+        cudaEvent_t e = g_prof.pool.back();
+        g_prof.pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+// Fold the recorded pairs of one class into ms_done (synchronises on them) and recycle the events.
+void prof_drain(int c) {
+    auto &v = g_prof.ev[c];
+    for (size_t i = 0; i + 1 < v.size(); i += 2) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(v[i + 1]) == cudaSuccess && cudaEventElapsedTime(&ms, v[i], v[i + 1]) == cudaSuccess) g_prof.ms_done[c] += ms;
+        g_prof.pool.push_back(v[i]);
+        g_prof.pool.push_back(v[i + 1]);
+    }
+    v.clear();
+}
+}  // namespace
+void prof_begin(int cls, int64_t units, cudaStream_t s) {
+    g_prof.launches[cls] += 1;
+    g_prof.units[cls] += units;
+    if (g_prof.mask >> cls & 1u) {
+        cudaEvent_t e = prof_event();
+        cudaEventRecord(e, s);
+        g_prof.ev[cls].push_back(e);
+    }
+}
+void prof_end(int cls, cudaStream_t s) {
+    if (g_prof.mask >> cls & 1u) {
+        cudaEvent_t e = prof_event();
+        cudaEventRecord(e, s);
+        g_prof.ev[cls].push_back(e);
+        if (g_prof.ev[cls].size() >= 16384) prof_drain(cls);  // bound the number of live events
+    }
+}
+}  // namespace linr
 
 // ---------------------------------------------------------------------------------------------- layout
 namespace {
@@ -161,12 +217,15 @@ template <int CIN, int COUT, int MODE>
 void launch_conv(const ConvArgs &a, int G, cudaStream_t s) {
     if (a.map.n_rows <= 0) return;
     dim3 grid((unsigned)ceil_div64(a.map.n_rows, CONV_TPB), (unsigned)G);
+    constexpr int cls = MODE == 2 ? K_CONVHEAD : MODE == 1 ? K_CONVBITS : (CIN == 8 ? (COUT == 8 ? K_CONV88 : K_CONV84) : (COUT == 8 ? K_CONV48 : K_CONV44));
+    ProfScope prof(cls, a.map.n_rows * G, s);
     conv27_kernel<CIN, COUT, MODE><<<grid, CONV_TPB, 0, s>>>(a);
 }
 template <int CIN, int COUT>
 void launch_pw(const PwArgs &a, int G, cudaStream_t s) {
     if (a.n_rows <= 0) return;
     dim3 grid((unsigned)ceil_div64(a.n_rows, PW_TPB), (unsigned)G);
+    ProfScope prof(K_PW, a.n_rows * G, s);
     pw_kernel<CIN, COUT><<<grid, PW_TPB, 0, s>>>(a);
 }
 
@@ -261,6 +320,8 @@ void launch_bwd_w(const RowMap &m, const NetWs &w, int P, const int *w_off, cons
     a.x = x, a.dy = dy, a.occ = occ, a.cin_base = cin_base, a.cin_step = cin_step;
     a.partial = w.partial, a.P = P, a.chunk = w.chunk;
     dim3 grid((unsigned)w.n_chunks, (unsigned)G);
+    constexpr int cls = MODE == 1 ? K_BWDWBITS : (COUT == 8 ? K_BWDW88 : (CIN == 8 ? K_BWDW84 : K_BWDW44));
+    ProfScope prof(cls, m.n_rows * G, s);
     conv27_bwd_w_kernel<CIN, COUT, MODE><<<grid, BWDW_TPB, 0, s>>>(a);
 }
 template <int CIN, int COUT>
@@ -271,6 +332,7 @@ void launch_pw_bwd_w(int64_t R, const NetWs &w, int P, const int *w_off, const i
     for (int g = 0; g < G; ++g) a.w_off[g] = w_off[g], a.b_off[g] = b_off[g];
     a.x = x, a.dy = dy, a.partial = w.partial, a.P = P, a.chunk = w.chunk;
     dim3 grid((unsigned)w.n_chunks, (unsigned)G);
+    ProfScope prof(K_PWBWDW, R * G, s);
     pw_bwd_w_kernel<CIN, COUT><<<grid, PWW_TPB, 0, s>>>(a);
 }
 
@@ -403,6 +465,25 @@ int linr_device_info(int device, int *sm_count, int64_t *l2_bytes) {
     return LINR_OK;
 }
 
+int linr_prof_enable(uint32_t class_mask) {
+    for (int c = 0; c < K_NCLASS; ++c) {
+        prof_drain(c);
+        g_prof.launches[c] = 0, g_prof.units[c] = 0, g_prof.ms_done[c] = 0.0;
+    }
+    g_prof.mask = class_mask;
+    return LINR_OK;
+}
+int linr_prof_read(int cls, double *ms_total, int64_t *launches, int64_t *units) {
+    LINR_REQUIRE(cls >= 0 && cls < K_NCLASS, "profiler class out of range");
+    prof_drain(cls);
+    if (ms_total) *ms_total = g_prof.ms_done[cls];
+    if (launches) *launches = g_prof.launches[cls];
+    if (units) *units = g_prof.units[cls];
+    return LINR_OK;
+}
+int linr_prof_classes(void) { return K_NCLASS; }
+const char *linr_prof_name(int cls) { return cls >= 0 && cls < K_NCLASS ? kNames[cls] : ""; }
+
 int64_t linr_param_count(int scale_num) {
     if (scale_num < 1 || scale_num > MAXS) return -1;
     return layout_for(scale_num).total;
@@ -439,6 +520,7 @@ int linr_net_forward(const float *d_params, int scale_num, const linr_rows *rows
     {  // SCE
         SceArgs a = sce_args(d_params, L, rows);
         a.f0 = T(w.f0, 0, 8);
+        ProfScope prof(K_SCE, R, s);
         sce_fwd_kernel<<<(unsigned)ceil_div64(R, SCE_TPB), SCE_TPB, 0, s>>>(a);
     }
     // GDFE: g = block_in(f0) -> hh[0]
@@ -451,7 +533,10 @@ int linr_net_forward(const float *d_params, int scale_num, const linr_rows *rows
     const bool want_bits = d_bits != nullptr || train;
     head_forward(d_params, L, m, 0, 8, T(w.hh, R * 8, 8), train ? w.hc : nullptr, rows->d_occ, d_probs, d_cdf,
                  train ? w.dzs : nullptr, loss_scale * 1.4426950408889634f, want_bits ? w.bits_partial : nullptr, 0, s);
-    if (d_bits) bits_finalize_kernel<<<1, 256, 0, s>>>(w.bits_partial, (int)ceil_div64(R, CONV_TPB) * 8, d_bits);
+    if (d_bits) {
+        ProfScope prof(K_REDUCE, 1, s);
+        bits_finalize_kernel<<<1, 256, 0, s>>>(w.bits_partial, (int)ceil_div64(R, CONV_TPB) * 8, d_bits);
+    }
     LINR_LAUNCH_CHECK();
     return LINR_OK;
 }
@@ -482,7 +567,11 @@ int linr_net_backward(const float *d_params, int scale_num, const linr_rows *row
         for (int k = 0; k < 8; ++k) a.w1_off[k] = L.mlp_w1[k], a.b1_off[k] = L.mlp_b1[k], a.w2_off[k] = L.mlp_w2[k], a.b2_off[k] = L.mlp_b2[k];
         a.c = T(w.hc, R * 8, 8), a.dz = w.dzs, a.dc = T(w.dc, R * 8, 8);
         a.partial = w.partial, a.P = P, a.chunk = w.chunk;
-        head_bwd_rows_kernel<<<dim3((unsigned)ceil_div64(R, 256), 8), 256, 0, s>>>(a);
+        {
+            ProfScope prof(K_HEADBWD, R * 8, s);
+            head_bwd_rows_kernel<<<dim3((unsigned)ceil_div64(R, 256), 8), 256, 0, s>>>(a);
+        }
+        ProfScope prof(K_HEADBWD, R * 8, s);
         head_bwd_w_kernel<<<dim3((unsigned)w.n_chunks, 8), 192, 0, s>>>(a);
     }
     launch_bwd_w<8, 8, 0>(m, w, P, L.pr_w, L.pr_b, 8, T(w.hh, R * 8, 8), T(w.dc, R * 8, 8), nullptr, 0, 0, s);
@@ -493,7 +582,10 @@ int linr_net_backward(const float *d_params, int scale_num, const linr_rows *row
         launch_conv<8, 8, 0>(a, 8, s);
     }
     // every h_k contains g: dg = sum_k dh_k
-    sum_groups_kernel<<<(unsigned)ceil_div64(R * 2, 256), 256, 0, s>>>(w.dhh, R * 8, 8, R * 2, w.dg);
+    {
+        ProfScope prof(K_REDUCE, R, s);
+        sum_groups_kernel<<<(unsigned)ceil_div64(R * 2, 256), 256, 0, s>>>(w.dhh, R * 8, 8, R * 2, w.dg);
+    }
     // LDFE blocks (inputs are occupancy bits: no input gradient)
     BlockBufs ob{w.ob_y, w.ob_t1, w.ob_t0, w.ob_t2, w.ob_z};
     BlockGrads gr{w.g_dz, w.g_dt0, w.g_dy, w.g_dt2, w.g_dt1};
@@ -504,10 +596,19 @@ int linr_net_backward(const float *d_params, int scale_num, const linr_rows *row
     // SCE
     SceArgs sa = sce_args(d_params, L, rows);
     sa.df0 = T(w.df0, 0, 8), sa.chunk = w.chunk;
-    sce_bwd_kernel<<<(unsigned)w.n_chunks, 256, 0, s>>>(sa, w.sce_rec);
-    sce_finalize_kernel<<<(unsigned)L.S, 256, 0, s>>>(sa, w.sce_rec, w.n_chunks, d_grad);
+    {
+        ProfScope prof(K_SCE, R, s);
+        sce_bwd_kernel<<<(unsigned)w.n_chunks, 256, 0, s>>>(sa, w.sce_rec);
+    }
+    {
+        ProfScope prof(K_SCE, L.S, s);
+        sce_finalize_kernel<<<(unsigned)L.S, 256, 0, s>>>(sa, w.sce_rec, w.n_chunks, d_grad);
+    }
     const int64_t cnt = P - L.conv_first;
-    finalize_grad_kernel<<<(unsigned)ceil_div64(cnt, 256), 256, 0, s>>>(w.partial, P, w.n_chunks, L.conv_first, cnt, d_grad);
+    {
+        ProfScope prof(K_REDUCE, cnt, s);
+        finalize_grad_kernel<<<(unsigned)ceil_div64(cnt, 256), 256, 0, s>>>(w.partial, P, w.n_chunks, L.conv_first, cnt, d_grad);
+    }
     LINR_LAUNCH_CHECK();
     return LINR_OK;
 }
@@ -527,7 +628,10 @@ int linr_net_decode_begin(const float *d_params, int scale_num, const linr_rows 
     const RowMap m = map_of(rows);
     SceArgs a = sce_args(d_params, L, rows);
     a.f0 = T(w.f0, 0, 8);
-    sce_fwd_kernel<<<(unsigned)ceil_div64(R, SCE_TPB), SCE_TPB, 0, s>>>(a);
+    {
+        ProfScope prof(K_SCE, R, s);
+        sce_fwd_kernel<<<(unsigned)ceil_div64(R, SCE_TPB), SCE_TPB, 0, s>>>(a);
+    }
     BlockBufs bi{w.bi_y, w.bi_t1, w.bi_t0, w.bi_t2, w.bi_z};
     block_forward(d_params, &L.bin, 1, m, false, nullptr, 0, 0, T(w.f0, 0, 8), bi, T(w.hh, 0, 8), TN(), s);
     LINR_LAUNCH_CHECK();
@@ -564,6 +668,7 @@ int linr_net_decode_stage(const float *d_params, int scale_num, const linr_rows 
 int linr_occ_set_stage(uint8_t *d_occ, const uint8_t *d_sym, int64_t n_rows, int stage, void *stream) {
     LINR_REQUIRE(stage >= 0 && stage < 8, "stage out of range");
     if (n_rows <= 0) return LINR_OK;
+    ProfScope prof(K_ADAM, n_rows, (cudaStream_t)stream);
     occ_set_stage_kernel<<<(unsigned)ceil_div64(n_rows, 256), 256, 0, (cudaStream_t)stream>>>(d_occ, d_sym, n_rows, stage);
     LINR_LAUNCH_CHECK();
     return LINR_OK;
@@ -625,8 +730,14 @@ int linr_spconv27_bwd_w(const float *d_x, int cin, const float *d_dy, int cout, 
     if (cin == 8 && cout == 8) launch_bwd_w<8, 8, 0>(m, w, P, wo, bo, 1, x, dy, nullptr, 0, 0, s);
     else if (cin == 8 && cout == 4) launch_bwd_w<8, 4, 0>(m, w, P, wo, bo, 1, x, dy, nullptr, 0, 0, s);
     else launch_bwd_w<4, 4, 0>(m, w, P, wo, bo, 1, x, dy, nullptr, 0, 0, s);
-    finalize_grad_kernel<<<(unsigned)ceil_div64(27 * cin * cout, 256), 256, 0, s>>>(w.partial, P, w.n_chunks, 0, 27 * cin * cout, d_dw);
-    if (d_dbias) finalize_grad_kernel<<<1, 256, 0, s>>>(w.partial, P, w.n_chunks, 27 * cin * cout, cout, d_dbias - 27 * cin * cout);
+    {
+        ProfScope prof(K_REDUCE, P, s);
+        finalize_grad_kernel<<<(unsigned)ceil_div64(27 * cin * cout, 256), 256, 0, s>>>(w.partial, P, w.n_chunks, 0, 27 * cin * cout, d_dw);
+    }
+    if (d_dbias) {
+        ProfScope prof(K_REDUCE, cout, s);
+        finalize_grad_kernel<<<1, 256, 0, s>>>(w.partial, P, w.n_chunks, 27 * cin * cout, cout, d_dbias - 27 * cin * cout);
+    }
     LINR_LAUNCH_CHECK();
     return LINR_OK;
 }
@@ -637,6 +748,7 @@ int linr_adam_fused(float *d_params, const float *d_grad, float *d_m, float *d_v
     if (n <= 0) return LINR_OK;
     const double bc1 = 1.0 - pow((double)beta1, (double)step);
     const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    ProfScope prof(K_ADAM, n, (cudaStream_t)stream);
     adam_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(d_params, d_grad, d_m, d_v, n, lr, beta1, beta2, eps,
                                                                                  weight_decay, (float)bc1, (float)sqrt(bc2));
     LINR_LAUNCH_CHECK();
@@ -646,6 +758,7 @@ int linr_adam_fused(float *d_params, const float *d_grad, float *d_m, float *d_v
 int linr_param_quant(const float *d_params, int64_t n, int bitdepth, uint8_t *d_q, float *d_recon, float *d_stats, void *stream) {
     LINR_REQUIRE(bitdepth >= 1 && bitdepth <= 8, "bitdepth must be in [1,8]");
     LINR_REQUIRE(n > 0, "empty parameter vector");
+    ProfScope prof(K_ADAM, n, (cudaStream_t)stream);
     quant_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_params, n, (float)((1 << bitdepth) - 1), d_q, d_recon, d_stats);
     LINR_LAUNCH_CHECK();
     return LINR_OK;

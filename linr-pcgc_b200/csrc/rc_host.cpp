@@ -130,12 +130,12 @@ struct Decoder {
     }
 };
 
-int64_t encode_binary(const uint16_t *mid, const uint8_t *sym, int64_t n, uint8_t *out, int64_t cap) {
+int64_t encode_binary(const uint16_t *mid, const uint8_t *sym, int shift, int64_t n, uint8_t *out, int64_t cap) {
     BitWriter w(out, cap);
     Coder c;
     for (int64_t i = 0; i < n; ++i) {
         const uint32_t m = mid[i];
-        if (sym[i] & 1u) c.narrow(m, 0x10000u, w);
+        if ((sym[i] >> shift) & 1u) c.narrow(m, 0x10000u, w);
         else c.narrow(0u, m, w);
     }
     c.flush(w);
@@ -147,7 +147,7 @@ int64_t encode_binary(const uint16_t *mid, const uint8_t *sym, int64_t n, uint8_
 extern "C" {
 
 int64_t linr_rc_encode_binary(const uint16_t *h_cdf_mid, const uint8_t *h_sym, int64_t n, uint8_t *h_out, int64_t cap) {
-    const int64_t need = encode_binary(h_cdf_mid, h_sym, n, h_out, cap);
+    const int64_t need = encode_binary(h_cdf_mid, h_sym, 0, n, h_out, cap);
     return need <= cap ? need : -need;
 }
 
@@ -170,7 +170,8 @@ int linr_rc_decode_binary(const uint16_t *h_cdf_mid, const uint8_t *h_in, int64_
 }
 
 int linr_rc_encode_binary_batch(int n_streams, const uint16_t *const *h_cdf_mid, const uint8_t *const *h_sym,
-                                const int64_t *n, uint8_t *const *h_out, const int64_t *cap, int64_t *h_written, int threads) {
+                                const int *h_shift, const int64_t *n, uint8_t *const *h_out, const int64_t *cap,
+                                int64_t *h_written, int threads) {
     if (n_streams <= 0) return LINR_OK;
     std::vector<int> order(n_streams);
     for (int i = 0; i < n_streams; ++i) order[i] = i;
@@ -181,7 +182,7 @@ int linr_rc_encode_binary_batch(int n_streams, const uint16_t *const *h_cdf_mid,
             const int j = next.fetch_add(1);
             if (j >= n_streams) return;
             const int i = order[j];
-            const int64_t need = encode_binary(h_cdf_mid[i], h_sym[i], n[i], h_out[i], cap[i]);
+            const int64_t need = encode_binary(h_cdf_mid[i], h_sym[i], h_shift ? (h_shift[i] & 7) : 0, n[i], h_out[i], cap[i]);
             h_written[i] = need <= cap[i] ? need : -need;
         }
     };

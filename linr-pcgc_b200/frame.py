@@ -38,6 +38,8 @@ class RowTables:
     mask: torch.Tensor
     occ: Optional[torch.Tensor] = None
     nbr27: Optional[torch.Tensor] = None
+    table: Optional[torch.Tensor] = None   # open-addressing hash (kept only on request)
+    cap: int = 0
     _rows: Optional[Rows] = field(default=None, repr=False)
 
     @property
@@ -57,7 +59,7 @@ class RowTables:
 
 
 def build_tables(coords: torch.Tensor, scale: torch.Tensor, occ: Optional[torch.Tensor] = None,
-                 dense: bool = False) -> RowTables:
+                 dense: bool = False, keep_hash: bool = False) -> RowTables:
     """Hash the rows and build the 27-neighbour kernel map (replaces ME's coordinate manager)."""
     lib = _lib.load()
     assert coords.is_cuda and coords.dtype == torch.int32 and coords.dim() == 2 and coords.shape[1] == 3
@@ -76,7 +78,19 @@ def build_tables(coords: torch.Tensor, scale: torch.Tensor, occ: Optional[torch.
     check(lib.linr_nbr_build(ptr(coords), ptr(scale), n, ptr(table), cap, ptr(nbr27) if dense else None, ptr(anchor), ld,
                              ptr(mask), ptr(nbr7), s), "linr_nbr_build")
     return RowTables(coords=coords, scale=scale, nbr7=nbr7[:n] if n else nbr7[:0], anchor=anchor, mask=mask[:n] if n else mask[:0],
-                     occ=occ, nbr27=nbr27)
+                     occ=occ, nbr27=nbr27, table=table if (keep_hash or dense) else None, cap=cap)
+
+
+def hash_lookup(t: RowTables, query: torch.Tensor, query_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """QuickSearchCoord.search_coord_idx (models/module_utils.py:276-283): row of each query coordinate or -1."""
+    lib = _lib.load()
+    if t.table is None:
+        raise _lib.LinrError("tables were built without keep_hash=True")
+    q = query.to(torch.int32).contiguous()
+    rows = torch.empty(int(q.shape[0]), dtype=torch.int32, device=q.device)
+    check(lib.linr_hash_lookup(ptr(q), ptr(query_scale), int(q.shape[0]), ptr(t.table), t.cap, ptr(rows), stream_ptr()),
+          "linr_hash_lookup")
+    return rows
 
 
 def sort_unique(xyz: torch.Tensor, bits: int) -> torch.Tensor:

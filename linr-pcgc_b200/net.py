@@ -107,3 +107,35 @@ def param_quant(params: torch.Tensor, bitdepth: int = 8):
     check(_lib.load().linr_param_quant(ptr(params), params.numel(), bitdepth, ptr(q), ptr(recon), ptr(stats), stream_ptr()),
           "linr_param_quant")
     return q, recon, stats
+
+
+# -- single-layer entry points (ME.MinkowskiConvolution, kernel_size 3, stride 1) ------------------------------
+def spconv27_fwd(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], t: RowTables, relu: bool = False):
+    """y = sum_k x[row(C+delta_k)] @ W[k] + bias  (models/upsample.py:17,90,95; models/resnet.py:15-51)."""
+    cin, cout = int(W.shape[1]), int(W.shape[2])
+    y = torch.empty((t.n_rows, cout), dtype=torch.float32, device=x.device)
+    rows = t.rows()
+    check(_lib.load().linr_spconv27_fwd(ptr(x.contiguous()), cin, ptr(W.contiguous()), ptr(bias), ptr(y), cout, C.byref(rows),
+                                        1 if relu else 0, stream_ptr()), "linr_spconv27_fwd")
+    return y
+
+
+def spconv27_bwd_in(dy: torch.Tensor, W: torch.Tensor, t: RowTables):
+    cin, cout = int(W.shape[1]), int(W.shape[2])
+    dx = torch.empty((t.n_rows, cin), dtype=torch.float32, device=dy.device)
+    rows = t.rows()
+    check(_lib.load().linr_spconv27_bwd_in(ptr(dy.contiguous()), cin, ptr(W.contiguous()), ptr(dx), cout, C.byref(rows),
+                                           stream_ptr()), "linr_spconv27_bwd_in")
+    return dx
+
+
+def spconv27_bwd_w(x: torch.Tensor, dy: torch.Tensor, t: RowTables):
+    lib = _lib.load()
+    cin, cout = int(x.shape[1]), int(dy.shape[1])
+    dW = torch.empty((27, cin, cout), dtype=torch.float32, device=x.device)
+    db = torch.empty(cout, dtype=torch.float32, device=x.device)
+    ws = torch.empty(int(lib.linr_spconv27_bwd_w_ws_bytes(t.n_rows, cin, cout)), dtype=torch.uint8, device=x.device)
+    rows = t.rows()
+    check(lib.linr_spconv27_bwd_w(ptr(x.contiguous()), cin, ptr(dy.contiguous()), cout, C.byref(rows), ptr(dW), ptr(db), ptr(ws),
+                                  ws.numel(), stream_ptr()), "linr_spconv27_bwd_w")
+    return dW, db

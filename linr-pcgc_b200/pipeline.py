@@ -1,0 +1,135 @@
+"""GOP-level public API: prepare -> overfit -> quantise model -> encode (-> decode), one call per GOP.
+
+Host-side mirror of the reference's orchestration for one GOP: `overfit_one_gop` (main.py:122-455),
+`encode_one_gop` (encoder.py:57-156) and `decode_one_gop` (decoder.py:51-147), minus the file IO (callers that want
+the reference's on-disk layout use `write_gop` / `read_gop`).  Everything a frame needs stays resident in HBM
+between epochs (the reference re-reads a pickle per iteration, datautils/custom_dataset.py:235-241).
+"""
+from __future__ import annotations
+
+import json
+import os
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import codec, model_compression
+from . import params as P
+from .frame import Frame, prepare_frame
+from .net import NetRunner
+from .trainer import GopTrainer, OptimState
+
+
+@dataclass
+class EncodedGop:
+    """What the reference writes under <encode_dir>/<gop>/ (encoder.py:84-146)."""
+    scale_num: int
+    side_info: Dict                      # mu, b, min_param, max_param, enc_mode, bitdepth  -> side_info.json
+    model_bytes: bytes                   # bins/model.bin
+    model_bits: float                    # bit_real of the model coder (model_size_est.py:489)
+    low_enc_bytes: bytes                 # bins/low_enc_bytes.bin
+    frame_bytes: List[List[bytes]]       # bins/frame%04d_scale%d.bin
+    point_nums: List[int]
+
+    @property
+    def total_bits(self) -> float:
+        return sum(8 * len(b) for fb in self.frame_bytes for b in fb) + self.model_bits + 8 * len(self.low_enc_bytes)
+
+    @property
+    def bpp(self) -> float:
+        """`real_bpp_all` accounting of test_utils.py:145-157."""
+        return self.total_bits / max(1, sum(self.point_nums))
+
+
+def prepare_gop(points: Sequence[torch.Tensor], scale_num: Optional[int] = None, min_point_num: int = 64,
+                device="cuda") -> List[Frame]:
+    """Upload (if on the host) and prepare every frame of a GOP.  `scale_num` None: discovered from the first frame
+    and then caps the others (main.py:77-78)."""
+    frames: List[Frame] = []
+    for p in points:
+        if not p.is_cuda:
+            p = p.to(device, non_blocking=True)
+        f = prepare_frame(p, scale_num, min_point_num)
+        if scale_num is None:
+            scale_num = f.n_scales
+        frames.append(f)
+    return frames
+
+
+def encode_gop(frames: Sequence[Frame], flat_params: torch.Tensor, scale_num: int, bitdepth: int = 8,
+               runner: Optional[NetRunner] = None, threads: Optional[int] = None) -> EncodedGop:
+    """Quantise the model, then code every frame with the *dequantised* parameters (encoder.py:101-103)."""
+    comp = model_compression.compress_model(flat_params, bitdepth)
+    recon = comp["recon_ret"]
+    if runner is None:
+        runner = NetRunner(scale_num, max(f.tables.n_rows for f in frames), flat_params.device, train=False)
+    frame_bytes = [codec.encode_frame(runner, recon, f, threads) for f in frames]
+    lows = [f.scale_coords(f.n_scales - 1).cpu().numpy() for f in frames]
+    low = codec.pack_low_xyz(lows, [f.coord_min for f in frames])
+    side = dict(mu=comp["mu"], b=comp["b"], min_param=comp["min_param"], max_param=comp["max_param"],
+                enc_mode=comp["enc_mode"], bitdepth=bitdepth)
+    return EncodedGop(scale_num, side, comp["final_bytes"], comp["bit_real"], low, frame_bytes, [f.point_num for f in frames])
+
+
+def decode_gop(enc: EncodedGop, device="cuda", runner: Optional[NetRunner] = None) -> List[torch.Tensor]:
+    """decode_one_gop (decoder.py:51-147): model from its bitstream, frames coarse-to-fine; returns the original
+    (min-restored) sorted coordinates of every frame as CUDA int32 [Np,3]."""
+    n = P.offsets(P.param_spec(enc.scale_num))[-1]
+    d = dict(enc.side_info)
+    d["final_bytes"] = enc.model_bytes
+    flat = model_compression.decompress_model(d, n, device)
+    lows, mins = codec.unpack_low_xyz(enc.low_enc_bytes)
+    if runner is None:
+        runner = NetRunner(enc.scale_num, 1, device, train=False)
+    out = []
+    for i, fb in enumerate(enc.frame_bytes):
+        low = torch.from_numpy(lows[i]).to(device)
+        xyz = codec.decode_frame(runner, flat, fb, low)
+        out.append(xyz + torch.from_numpy(mins[i].copy()).to(device))
+    return out
+
+
+def overfit_encode_gop(points: Sequence[torch.Tensor], epochs: int, state: Optional[OptimState] = None,
+                       scale_num: Optional[int] = None, min_point_num: int = 64, bitdepth: int = 8, device="cuda",
+                       seed: Optional[int] = None, trainer_kwargs: Optional[Dict] = None, threads: Optional[int] = None):
+    """The whole per-GOP hot path from raw points (host or device) to bitstreams.
+    Returns (EncodedGop, OptimState to seed the next GOP, per-epoch losses)."""
+    frames = prepare_gop(points, scale_num, min_point_num, device)
+    S = scale_num or frames[0].n_scales
+    tr = GopTrainer(S, device, seed=seed, state=state, max_rows=max(f.tables.n_rows for f in frames), **(trainer_kwargs or {}))
+    losses = tr.fit(frames, epochs)
+    enc = encode_gop(frames, tr.state.params, S, bitdepth, threads=threads)
+    return enc, tr.state, losses
+
+
+# ---- the reference's on-disk layout (encoder.py:13-18,84-146) ---------------------------------------------------
+def write_gop(enc: EncodedGop, gop_dir: str):
+    bins = os.path.join(gop_dir, "bins")
+    os.makedirs(bins, exist_ok=True)
+    with open(os.path.join(bins, "low_enc_bytes.bin"), "wb") as f:
+        f.write(enc.low_enc_bytes)
+    with open(os.path.join(bins, "model.bin"), "wb") as f:
+        f.write(enc.model_bytes)
+    with open(os.path.join(gop_dir, "side_info.json"), "w") as f:
+        json.dump(enc.side_info, f, indent=4)
+    for i, fb in enumerate(enc.frame_bytes):
+        for s, b in enumerate(fb):
+            with open(os.path.join(bins, f"frame{i:04d}_scale{s}.bin"), "wb") as f:
+                f.write(b)
+
+
+def read_gop(gop_dir: str, scale_num: int, n_frames: int) -> EncodedGop:
+    bins = os.path.join(gop_dir, "bins")
+    with open(os.path.join(gop_dir, "side_info.json")) as f:
+        side = json.load(f)
+    rd = lambda n: open(os.path.join(bins, n), "rb").read()
+    frame_bytes = []
+    for i in range(n_frames):
+        fb, s = [], 0
+        while os.path.exists(os.path.join(bins, f"frame{i:04d}_scale{s}.bin")):
+            fb.append(rd(f"frame{i:04d}_scale{s}.bin"))
+            s += 1
+        frame_bytes.append(fb)
+    return EncodedGop(scale_num, side, rd("model.bin"), 0.0, rd("low_enc_bytes.bin"), frame_bytes, [0] * n_frames)

@@ -42,8 +42,11 @@ def decode_binary(cdf_mid: np.ndarray, data: bytes, n: int) -> np.ndarray:
     return out
 
 
-def encode_binary_batch(cdf_mids: Sequence[np.ndarray], syms: Sequence[np.ndarray], threads: int | None = None) -> List[bytes]:
-    """Independent streams (8 stages x S scales of a frame) on a pool of host threads."""
+def encode_binary_batch(cdf_mids: Sequence[np.ndarray], syms: Sequence[np.ndarray], shifts: Sequence[int] | None = None,
+                        threads: int | None = None) -> List[bytes]:
+    """Independent streams (8 stages x S scales of a frame) on a pool of host threads.
+
+    Stream i codes bit `shifts[i]` of every byte of `syms[i]` (packed occupancy), default bit 0."""
     lib = _lib.load()
     k = len(cdf_mids)
     if k == 0:
@@ -52,6 +55,7 @@ def encode_binary_batch(cdf_mids: Sequence[np.ndarray], syms: Sequence[np.ndarra
     cdf_mids = [np.ascontiguousarray(c).view(np.uint16) for c in cdf_mids]
     syms = [np.ascontiguousarray(s, dtype=np.uint8) for s in syms]
     ns = np.array([len(s) for s in syms], dtype=np.int64)
+    sh = np.zeros(k, dtype=np.int32) if shifts is None else np.asarray(shifts, dtype=np.int32)
     caps = ns // 4 + 64
     while True:
         outs = [np.empty(int(c), dtype=np.uint8) for c in caps]
@@ -59,7 +63,7 @@ def encode_binary_batch(cdf_mids: Sequence[np.ndarray], syms: Sequence[np.ndarra
         sp = (C.c_void_p * k)(*[s.ctypes.data for s in syms])
         op = (C.c_void_p * k)(*[o.ctypes.data for o in outs])
         written = np.zeros(k, dtype=np.int64)
-        rc = lib.linr_rc_encode_binary_batch(k, cp, sp, _p(ns), op, _p(caps), _p(written), threads)
+        rc = lib.linr_rc_encode_binary_batch(k, cp, sp, _p(sh), _p(ns), op, _p(caps), _p(written), threads)
         if rc == 0:
             return [outs[i][: int(written[i])].tobytes() for i in range(k)]
         caps = np.maximum(caps, np.abs(written))

@@ -1,0 +1,348 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures recorded from the
+reference's own Python.  Integer / byte / index results bit-exact; fp32 results within 1e-4 relative
+(BASELINE.json north_star), tolerance written at each assert."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4  # north_star: logits and losses within 1e-4 relative (fp32)
+
+
+@pytest.fixture(scope="module")
+def L():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import linr_pcgc_b200 as pkg
+    from linr_pcgc_b200 import _lib, codec, frame, net, rc, synth
+    _lib.load()  # raises if the extension is missing: there is no fallback
+
+    class NS:
+        pass
+
+    ns = NS()
+    ns.frame, ns.net, ns.codec, ns.rc, ns.synth, ns.lib = frame, net, codec, rc, synth, _lib
+    return ns
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import linr_oracle
+    return linr_oracle
+
+
+def _load(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+def _cuda(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def _dense_from_compact(anchor, mask, n):
+    """Expand (anchor [9,ld], mask [n]) to the dense [n,27] table: present rows of a column are consecutive."""
+    anchor = anchor.cpu().numpy()
+    mask = mask.cpu().numpy().astype(np.uint32)
+    out = -np.ones((n, 27), dtype=np.int32)
+    for c in range(9):
+        run = np.zeros(n, dtype=np.int32)
+        for j in range(3):
+            bit = (mask >> np.uint32(3 * c + j)) & 1
+            out[:, c + 9 * j] = np.where(bit == 1, anchor[c, :n] + run, -1)
+            run += bit.astype(np.int32)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ coordinate stage
+@pytest.mark.parametrize("name", ["tiny", "tiny_s3", "ragged", "mid"])
+def test_prepare_frame_bit_exact(L, O, name):
+    g = _load(f"int_{name}.npz")
+    scale_num = int(g["scale_num"]) if name == "tiny_s3" else None
+    fr = L.frame.prepare_frame(_cuda(g["points"]), scale_num, int(g["min_point_num"]), dense=True)
+    assert fr.n_scales == int(g["n_scales"])
+    assert fr.point_num == int(g["point_num"])
+    assert (fr.coord_min == g["coord_min"]).all()
+    assert (fr.xyz.cpu().numpy() == g["ori"]).all()
+    for s in range(fr.n_scales):
+        a, b = fr.scale_off[s], fr.scale_off[s + 1]
+        coord = fr.scale_coords(s).cpu().numpy()
+        assert (coord == g[f"s{s}_coord"]).all()
+        occ = fr.scale_occ(s).cpu().numpy()
+        ref_occ = (g[f"s{s}_occ"].astype(np.uint32) << np.arange(8, dtype=np.uint32)).sum(axis=1).astype(np.uint8)
+        assert (occ == ref_occ).all()
+        nb7 = fr.scale_nbr7(s).cpu().numpy()
+        ref7 = (g[f"s{s}_nbr7"].astype(np.uint32) << np.arange(7, dtype=np.uint32)).sum(axis=1).astype(np.uint8)
+        assert (nb7 == ref7).all()
+        # kernel map: dense table vs oracle (rows are local to the scale in the oracle, global in the frame tables)
+        ref27 = O.nbr27(coord)
+        got27 = fr.tables.nbr27[a:b].cpu().numpy()
+        assert (np.where(got27 >= 0, got27 - a, -1) == ref27).all()
+        # upper_layer round trip (datautils/custom_dataset.py:295)
+        up = L.frame.octree_up(fr.scale_coords(s), fr.scale_occ(s), fr.bits)
+        assert (up.cpu().numpy() == g[f"s{s}_up"]).all()
+    n = fr.tables.n_rows
+    assert (_dense_from_compact(fr.tables.anchor, fr.tables.mask, n) == fr.tables.nbr27.cpu().numpy()).all()
+
+
+def test_sort_unique_lookup_bit_exact(L, O):
+    g = _load("int_sort.npz")
+    xyz = g["xyz"].astype(np.int64)
+    lo = xyz.min()
+    shifted = _cuda((xyz - lo).astype(np.int32))  # the ABI takes non-negative coordinates
+    srt = L.frame.sort_rows(shifted, 8).cpu().numpy() + lo
+    assert (srt == g["sorted"]).all()
+    uq = L.frame.sort_unique(shifted, 8).cpu().numpy() + lo
+    assert (uq == g["uniq"]).all()
+    # quantize(.,2) = unique(floor(x/2)) (models/quantize_functions.py:19-30): floor on the original values
+    q2 = L.frame.sort_unique(_cuda(((xyz >> 1) - (lo >> 1)).astype(np.int32)), 8).cpu().numpy() + (lo >> 1)
+    assert (q2 == g["quant2"]).all()
+    # QuickSearchCoord.search / search_coord_idx (models/module_utils.py:260-318) via the hash
+    uq_t = _cuda((g["uniq"].astype(np.int64) - lo + 1).astype(np.int32))
+    sc = torch.zeros(len(uq_t), dtype=torch.uint8, device="cuda")
+    t = L.frame.build_tables(uq_t, sc)
+    for qname, want_idx in (("query", None), ("query_idx_clamped", g["idx"])):
+        q = _cuda((g[qname].astype(np.int64) - lo + 1).astype(np.int32))
+        rows = L.frame.hash_lookup(t, q)
+        if want_idx is None:
+            assert ((rows.cpu().numpy() >= 0).astype(np.uint8) == g["hit"]).all()
+        else:
+            assert (rows.cpu().numpy() == want_idx).all()
+
+
+def test_empty_and_single_point(L):
+    one = torch.tensor([[5, 6, 7]], dtype=torch.int32, device="cuda")
+    fr = L.frame.prepare_frame(one, None, 64)
+    assert fr.n_scales == 1 and fr.point_num == 1
+    assert fr.scale_occ(0).cpu().tolist() == [1]  # after min subtraction the point is (0,0,0): octant 0
+    up = L.frame.octree_up(fr.scale_coords(0), fr.scale_occ(0), 4)
+    assert up.cpu().tolist() == [[0, 0, 0]]
+    empty = torch.zeros((0, 3), dtype=torch.int32, device="cuda")
+    assert L.frame.sort_unique(empty, 4).shape[0] == 0
+    with pytest.raises(L.lib.LinrError):
+        L.frame.prepare_frame(empty, None, 64)
+    with pytest.raises(L.lib.LinrError):
+        L.frame.prepare_frame(torch.zeros((4, 3), dtype=torch.int32), None, 64)  # host tensor: no CPU path
+
+
+@pytest.mark.parametrize("shape,bits", [("loot", 10), ("owlii", 11)])
+def test_full_size_octree_round_trip(L, shape, bits):
+    """BASELINE.json full sizes: size-independent properties (round trip, sortedness, idempotence)."""
+    pts = L.synth.make_sequence(shape, 1, device="cuda")[0]
+    perm = torch.randperm(pts.shape[0], device="cuda")
+    fr = L.frame.prepare_frame(torch.cat([pts[perm], pts[perm[:1000]]]), None, 64)  # shuffled + duplicates
+    assert fr.point_num == pts.shape[0]
+    assert (fr.xyz + torch.from_numpy(fr.coord_min).cuda() == pts).all()
+    assert fr.n_scales == (7 if shape == "loot" else 8)
+    child = fr.xyz
+    for s in range(fr.n_scales):
+        c = fr.scale_coords(s).to(torch.int64)
+        key = (c[:, 0] << 42) | (c[:, 1] << 21) | c[:, 2]
+        assert (key[1:] > key[:-1]).all()  # strictly sorted = unique
+        up = L.frame.octree_up(fr.scale_coords(s), fr.scale_occ(s), fr.bits)
+        assert up.shape == child.shape and (up == child).all()
+        again = L.frame.sort_unique(fr.scale_coords(s), fr.bits)
+        assert (again == fr.scale_coords(s)).all()
+        child = fr.scale_coords(s)
+    # kernel map symmetry: pair (i -> o, k) <=> (o -> i, 26-k)
+    n = fr.scale_off[1]
+    sc = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    t = L.frame.build_tables(fr.scale_coords(0).contiguous(), sc, dense=True)
+    nb = t.nbr27.to(torch.int64)
+    assert (nb[:, 13] == torch.arange(n, device="cuda")).all()
+    for k in (0, 5, 12, 22, 26):
+        o = torch.nonzero(nb[:, k] >= 0)[:, 0]
+        assert (nb[nb[o, k], 26 - k] == o).all()
+    assert int(fr.scale_coords(fr.n_scales - 1).max()) < 256  # test_utils.py:221
+
+
+# ------------------------------------------------------------------------------------------------ network
+def _net_case(L, O):
+    g = _load("net_tiny.npz")
+    S = int(g["scale_num"])
+    sd = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w:")}
+    flat = O.flatten_params(sd, S).contiguous()
+    assert flat.numel() == L.net.param_count(S)
+    fr = L.frame.prepare_frame(_cuda(g["points"]), None, 64)
+    return g, S, sd, flat, fr
+
+
+def test_param_layout_matches_checkpoint_contract(L, O):
+    for S in (3, 7, 8):
+        spec = O.param_spec(S)
+        offs = L.net.param_offsets(S)
+        want, o = [], 0
+        for _, shp in spec:
+            want.append(o)
+            o += int(np.prod(shp))
+        assert offs == want and L.net.param_count(S) == o
+    assert L.net.param_count(7) == 54712
+
+
+def test_forward_probs_bits_cdf(L, O):
+    g, S, sd, flat, fr = _net_case(L, O)
+    run = L.net.NetRunner(S, fr.tables.n_rows, "cuda", train=False)
+    out = run.forward(flat.cuda(), fr.tables, want_probs=True, want_cdf=True, want_bits=True)
+    probs = out["probs"].cpu().numpy()
+    bits = float(out["bits"].item())
+    assert abs(bits - float(g["bits"])) <= RTOL * float(g["bits"])
+    for s in range(fr.n_scales):
+        a, b = fr.scale_off[s], fr.scale_off[s + 1]
+        np.testing.assert_allclose(probs[:, a:b].T, g[f"s{s}_probs"], rtol=RTOL, atol=1e-6)
+    # 16-bit CDF boundary = torchac's conversion of the GPU's own probability, bit-exact
+    cdf = out["cdf"].cpu().numpy().view(np.uint16)
+    assert (cdf == O.cdf_u16_binary(probs.reshape(-1)).reshape(cdf.shape)).all()
+
+
+def test_backward_adam_match_and_deterministic(L, O):
+    g, S, sd, flat, fr = _net_case(L, O)
+    P = flat.numel()
+    run = L.net.NetRunner(S, fr.tables.n_rows, "cuda", train=True)
+    params = flat.cuda()
+    grads = []
+    for _ in range(2):
+        grad = torch.full((P,), float("nan"), device="cuda")
+        out = run.forward(params, fr.tables, train=True, loss_scale=1.0 / fr.point_num)
+        run.backward(params, fr.tables, grad)
+        grads.append(grad.cpu().numpy())
+    assert np.array_equal(grads[0], grads[1])  # run-to-run bitwise reproducible (no fp atomics)
+    ref = g["grad_flat"]
+    assert np.isfinite(grads[0]).all()
+    # per tensor: max abs error relative to the tensor's own scale
+    offs = L.net.param_offsets(S) + [P]
+    names = [n for n, _ in O.param_spec(S)]
+    for i, n in enumerate(names):
+        a, b = offs[i], offs[i + 1]
+        scale = max(np.abs(ref[a:b]).max(), 1e-6 * np.abs(ref).max())
+        err = np.abs(grads[0][a:b] - ref[a:b]).max() / scale
+        assert err < 5e-4, (n, err)
+    assert np.abs(grads[0] - ref).max() / np.abs(ref).max() < RTOL
+    # Adam (main.py:231-237), one step from zero moments, fed the recorded gradient
+    m = torch.zeros(P, device="cuda")
+    v = torch.zeros(P, device="cuda")
+    p2 = params.clone()
+    L.net.adam_step(p2, _cuda(ref), m, v, 1, 0.01)
+    np.testing.assert_allclose(p2.cpu().numpy(), g["flat_after_adam"], rtol=1e-5, atol=1e-6)
+
+
+def test_param_quant_bit_exact(L, O):
+    g, S, sd, flat, fr = _net_case(L, O)
+    q, recon, stats = L.net.param_quant(flat.cuda(), 8)
+    np.testing.assert_array_equal(recon.cpu().numpy(), g["q_recon"])
+    st = stats.cpu().numpy()
+    assert st[0] == g["q_min"] and st[1] == g["q_max"] and st[2] == g["q_mu"] and st[3] == g["q_b"]
+    qo, _, _, _ = O.quant_uniform2(flat, 8)
+    np.testing.assert_array_equal(q.cpu().numpy(), qo.numpy().astype(np.uint8))
+
+
+def test_single_layer_conv_entry_points(L, O):
+    g = _load("int_mid.npz")
+    coord = g["s0_coord"]
+    n = len(coord)
+    t = L.frame.build_tables(_cuda(coord), torch.zeros(n, dtype=torch.uint8, device="cuda"), dense=True)
+    nbr = t.nbr27.cpu().to(torch.int64)
+    gen = torch.Generator().manual_seed(5)
+    for cin, cout in ((8, 8), (8, 4), (4, 4), (4, 8)):
+        x = torch.randn(n, cin, generator=gen)
+        W = torch.randn(27, cin, cout, generator=gen) * 0.2
+        b = torch.randn(cout, generator=gen)
+        ref = O.conv27(x, nbr, W, b)
+        y = L.net.spconv27_fwd(x.cuda(), W.cuda(), b.cuda(), t)
+        np.testing.assert_allclose(y.cpu().numpy(), ref.numpy(), rtol=RTOL, atol=1e-5)
+        # autograd of the oracle conv gives the reference gradients
+        xr, Wr = x.clone().requires_grad_(True), W.clone().requires_grad_(True)
+        dy = torch.randn(n, cout, generator=gen)
+        O.conv27(xr, nbr, Wr, b).backward(dy)
+        dx = L.net.spconv27_bwd_in(dy.cuda(), W.cuda(), t)
+        np.testing.assert_allclose(dx.cpu().numpy(), xr.grad.numpy(), rtol=RTOL, atol=1e-5)
+        if (cin, cout) != (4, 8):
+            dW, db = L.net.spconv27_bwd_w(x.cuda(), dy.cuda(), t)
+            sc = Wr.grad.abs().max().item()
+            assert (dW.cpu() - Wr.grad).abs().max().item() / sc < RTOL
+            np.testing.assert_allclose(db.cpu().numpy(), dy.sum(0).numpy(), rtol=RTOL, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ coding
+def test_encode_decode_lossless_and_bpp(L, O):
+    g, S, sd, flat, fr = _net_case(L, O)
+    params = flat.cuda()
+    run = L.net.NetRunner(S, fr.tables.n_rows, "cuda", train=False)
+    all_bytes = L.codec.encode_frame(run, params, fr)
+    tot = sum(len(b) for b in all_bytes) * 8
+    # bpp within 0.5 % of the reference flow's bitstream (north_star)
+    assert abs(tot - int(g["all_bit"])) <= 0.005 * int(g["all_bit"])
+    for s, b in enumerate(all_bytes):
+        assert abs(len(b) - len(g[f"s{s}_bytes"])) <= max(2, 0.005 * len(g[f"s{s}_bytes"]))
+    low = fr.scale_coords(fr.n_scales - 1).contiguous()
+    dec = L.codec.decode_frame(run, params, all_bytes, low)
+    assert dec.shape == fr.xyz.shape and (dec == fr.xyz).all()  # decoder.py:140
+    assert (dec.cpu().numpy() == g["dec_coord"]).all()
+    # the product's host coder is bitstream-compatible with the oracle's torchac restatement
+    from oracle import rc as orc
+    cdf, occ, R = L.codec.frame_cdfs_to_host(run, params, fr)
+    a, b = fr.scale_off[0], fr.scale_off[1]
+    for k in (0, 7):
+        sym = ((occ[a:b] >> k) & 1).astype(np.int16)
+        n = b - a
+        rows = np.stack([np.zeros(n, np.uint16), cdf[k, a:b], np.zeros(n, np.uint16)], axis=1)
+        want = orc.encode_u16(rows, sym)
+        got = L.codec.unpack_bitstream(all_bytes[0])[k]
+        assert got == want
+        assert (orc.decode_u16(rows, got, n) == sym).all()
+
+
+def test_batched_and_sequential_cdfs_identical(L, O):
+    """Encoder (teacher-forced, all scales in one launch set) and decoder (per scale, stage by stage) must see
+    bit-identical 16-bit CDFs: the precondition of lossless decoding."""
+    g, S, sd, flat, fr = _net_case(L, O)
+    params = flat.cuda()
+    run = L.net.NetRunner(S, fr.tables.n_rows, "cuda", train=False)
+    enc = run.forward(params, fr.tables, want_cdf=True, want_probs=True, want_bits=False)
+    enc_cdf = enc["cdf"].clone()
+    enc_p = enc["probs"].clone()
+    run2 = L.net.NetRunner(S, fr.tables.n_rows, "cuda", train=False)
+    for s in range(fr.n_scales):
+        a, b = fr.scale_off[s], fr.scale_off[s + 1]
+        n = b - a
+        t = L.frame.build_tables(fr.scale_coords(s).contiguous(), torch.full((n,), s, dtype=torch.uint8, device="cuda"),
+                                 fr.scale_occ(s).contiguous())
+        run2.decode_begin(params, t)
+        for k in range(8):
+            cdf_k, p_k = run2.decode_stage(params, t, k, want_probs=True)
+            assert torch.equal(cdf_k, enc_cdf[k, a:b])
+            assert torch.equal(p_k, enc_p[k, a:b])
+
+
+def test_rc_edges(L):
+    rng = np.random.default_rng(11)
+    for n in (0, 1, 7, 4097):
+        cdf = rng.integers(1, 65536, size=n).astype(np.uint16)
+        cdf[: n // 8] = 1
+        cdf[n // 8: n // 4] = 65535
+        sym = rng.integers(0, 2, size=n).astype(np.uint8)
+        b = L.rc.encode_binary(cdf, sym)
+        assert (L.rc.decode_binary(cdf, b, n) == sym).all()
+    packed = rng.integers(0, 256, size=1000).astype(np.uint8)
+    cdfs = [rng.integers(1, 65536, size=1000).astype(np.uint16) for _ in range(8)]
+    outs = L.rc.encode_binary_batch(cdfs, [packed] * 8, list(range(8)), threads=4)
+    for k in range(8):
+        assert outs[k] == L.rc.encode_binary(cdfs[k], (packed >> k) & 1)
+
+
+def test_full_size_encode_decode_lossless(L, O):
+    """loot-sized frame (~780k points, 7 scales, 2.3 M symbols): encode -> decode round trip, random-init model."""
+    pts = L.synth.make_sequence("loot", 1, device="cuda")[0]
+    fr = L.frame.prepare_frame(pts, None, 64)
+    S = fr.n_scales
+    flat = O.flatten_params(O.init_params(S, seed=3), S).cuda()
+    run = L.net.NetRunner(S, fr.tables.n_rows, "cuda", train=False)
+    all_bytes = L.codec.encode_frame(run, flat, fr)
+    dec = L.codec.decode_frame(run, flat, all_bytes, fr.scale_coords(S - 1).contiguous())
+    assert dec.shape == fr.xyz.shape and (dec == fr.xyz).all()
