@@ -107,7 +107,7 @@ def test_sort_unique_lookup_bit_exact(L, O):
     # QuickSearchCoord.search / search_coord_idx (models/module_utils.py:260-318) via the hash
     uq_t = _cuda((g["uniq"].astype(np.int64) - lo + 1).astype(np.int32))
     sc = torch.zeros(len(uq_t), dtype=torch.uint8, device="cuda")
-    t = L.frame.build_tables(uq_t, sc)
+    t = L.frame.build_tables(uq_t, sc, keep_hash=True)
     for qname, want_idx in (("query", None), ("query_idx_clamped", g["idx"])):
         q = _cuda((g[qname].astype(np.int64) - lo + 1).astype(np.int32))
         rows = L.frame.hash_lookup(t, q)
