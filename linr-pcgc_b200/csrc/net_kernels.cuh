@@ -72,13 +72,37 @@ struct ConvArgs {
 };
 
 constexpr int CONV_TPB = 128;
+constexpr int CONV_RPT = 2;                       // rows per thread (weights read from shared memory once for both)
+constexpr int CONV_ROWS = CONV_TPB * CONV_RPT;    // rows per block
+
+// Packed fp32x2 FMA (Blackwell FFMA2): two independent IEEE fp32 FMAs per instruction, so results are bit-identical
+// to scalar fmaf; `pack2(x, x)` compiles to the scalar-broadcast operand form (no extra moves).
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b) {
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 
 template <int CIN, int COUT, int MODE>
 __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
     constexpr int WMAX = (MODE == 1) ? 27 * 7 * COUT : 27 * CIN * COUT;
+    constexpr int HQ = COUT / 2;  // accumulator pairs per row
     __shared__ __align__(16) float s_w[WMAX];
     __shared__ float s_b[COUT];
-    __shared__ float s_head[(MODE == 2) ? (24 * 8 + 24 + 24 + 1) : 1];
+    // head (MODE 2): W1 transposed [8][24] so that hidden-unit pairs are adjacent, then b1[24], w2[24], b2
+    __shared__ __align__(16) float s_head[(MODE == 2) ? (24 * 8 + 24 + 24 + 4) : 4];
     __shared__ float s_red[CONV_TPB / 32];
     const int g = blockIdx.y;
     const int cin = (MODE == 1) ? (a.cin_base + g * a.cin_step) : CIN;
@@ -97,7 +121,7 @@ __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
         if (threadIdx.x < COUT)
             s_b[threadIdx.x] = a.bias_direct ? a.bias_direct[threadIdx.x] : (a.b_off[g] >= 0 ? a.params[a.b_off[g] + threadIdx.x] : 0.f);
         if (MODE == 2) {
-            for (int i = threadIdx.x; i < 24 * 8; i += CONV_TPB) s_head[i] = a.params[a.w1_off[g] + i];
+            for (int i = threadIdx.x; i < 24 * 8; i += CONV_TPB) s_head[(i & 7) * 24 + (i >> 3)] = a.params[a.w1_off[g] + i];
             if (threadIdx.x < 24) {
                 s_head[192 + threadIdx.x] = a.params[a.b1_off[g] + threadIdx.x];
                 s_head[216 + threadIdx.x] = a.params[a.w2_off[g] + threadIdx.x];
@@ -106,99 +130,154 @@ __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
         }
     }
     __syncthreads();
-    const int64_t row = blockIdx.x * (int64_t)CONV_TPB + threadIdx.x;
-    const bool live = row < a.map.n_rows;
-    float bits = 0.f;
-    if (live) {
-        float acc[COUT];
+
+    int64_t row[CONV_RPT];
+    bool live[CONV_RPT];
+    uint32_t m[CONV_RPT];
+    u64 acc[CONV_RPT][HQ];
 #pragma unroll
-        for (int i = 0; i < COUT; ++i) acc[i] = 0.f;
-        const uint32_t m = a.map.mask[row];
+    for (int r = 0; r < CONV_RPT; ++r) {
+        row[r] = blockIdx.x * (int64_t)CONV_ROWS + r * CONV_TPB + threadIdx.x;
+        live[r] = row[r] < a.map.n_rows;
+        m[r] = live[r] ? a.map.mask[row[r]] : 0u;
+#pragma unroll
+        for (int q = 0; q < HQ; ++q) acc[r][q] = 0ull;
+    }
 #pragma unroll 1
-        for (int c = 0; c < 9; ++c) {
-            const uint32_t m3 = (m >> (3 * c)) & 7u;
-            if (m3 == 0) continue;
-            int nb = a.map.anchor[c * a.map.ld + row];
+    for (int c = 0; c < 9; ++c) {
+        uint32_t m3[CONV_RPT];
+        int nb[CONV_RPT];
+        uint32_t any = 0;
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                if ((m3 >> j) & 1u) {
-                    const float *wk = s_w + (c + 9 * j) * cin * COUT;
-                    if (MODE == 1) {
-                        const unsigned o = a.occ[nb];
+        for (int r = 0; r < CONV_RPT; ++r) {
+            m3[r] = (m[r] >> (3 * c)) & 7u;
+            any |= m3[r];
+            nb[r] = m3[r] ? a.map.anchor[c * a.map.ld + row[r]] : 0;
+        }
+        if (any == 0) continue;
 #pragma unroll
-                        for (int ci = 0; ci < 7; ++ci) {
-                            if (ci < cin && ((o >> ci) & 1u)) {
+        for (int j = 0; j < 3; ++j) {
+            if (!((any >> j) & 1u)) continue;
+            const float *wk = s_w + (c + 9 * j) * cin * COUT;
+            bool on[CONV_RPT];
+            float xv[CONV_RPT][CIN];
+            unsigned ob[CONV_RPT];
 #pragma unroll
-                                for (int co = 0; co < COUT; ++co) acc[co] += wk[ci * COUT + co];
+            for (int r = 0; r < CONV_RPT; ++r) {
+                on[r] = (m3[r] >> j) & 1u;
+                ob[r] = 0;
+                if (on[r]) {
+                    if (MODE == 1) ob[r] = a.occ[nb[r]];
+                    else load_row<CIN>(tptr(a.x, g, nb[r]), xv[r]);
+                    ++nb[r];
+                }
+            }
+            if (MODE == 1) {
+                // input channel ci = bit ci of the neighbour's occupancy byte ({0,1}): acc += w (same rounding as fma(1,w,acc))
+#pragma unroll
+                for (int ci = 0; ci < 7; ++ci) {
+                    if (ci < cin) {
+                        const ulonglong2 *w2 = reinterpret_cast<const ulonglong2 *>(wk + ci * COUT);
+                        u64 wq[HQ];
+#pragma unroll
+                        for (int q = 0; q < HQ; q += 2) {
+                            const ulonglong2 t = w2[q >> 1];
+                            wq[q] = t.x, wq[q + 1] = t.y;
+                        }
+#pragma unroll
+                        for (int r = 0; r < CONV_RPT; ++r) {
+                            if (on[r] && ((ob[r] >> ci) & 1u)) {
+#pragma unroll
+                                for (int q = 0; q < HQ; ++q) acc[r][q] = fadd2(acc[r][q], wq[q]);
                             }
                         }
-                    } else {
-                        float xv[CIN];
-                        load_row<CIN>(tptr(a.x, g, nb), xv);
+                    }
+                }
+            } else {
 #pragma unroll
-                        for (int ci = 0; ci < CIN; ++ci) {
+                for (int ci = 0; ci < CIN; ++ci) {
+                    const ulonglong2 *w2 = reinterpret_cast<const ulonglong2 *>(wk + ci * COUT);
+                    u64 wq[HQ];
 #pragma unroll
-                            for (int co = 0; co < COUT; ++co) acc[co] = fmaf(xv[ci], wk[ci * COUT + co], acc[co]);
+                    for (int q = 0; q < HQ; q += 2) {
+                        const ulonglong2 t = w2[q >> 1];
+                        wq[q] = t.x, wq[q + 1] = t.y;
+                    }
+#pragma unroll
+                    for (int r = 0; r < CONV_RPT; ++r) {
+                        if (on[r]) {
+                            const u64 xx = pack2(xv[r][ci], xv[r][ci]);
+#pragma unroll
+                            for (int q = 0; q < HQ; ++q) acc[r][q] = ffma2(xx, wq[q], acc[r][q]);
                         }
                     }
-                    ++nb;
                 }
             }
         }
-#pragma unroll
-        for (int co = 0; co < COUT; ++co) acc[co] += s_b[co];
+    }
 
+    float bits = 0.f;
+#pragma unroll
+    for (int r = 0; r < CONV_RPT; ++r) {
+        if (!live[r]) continue;
+        float o[COUT];
+#pragma unroll
+        for (int q = 0; q < HQ; ++q) unpack2(acc[r][q], o[2 * q], o[2 * q + 1]);
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) o[co] += s_b[co];
         if (MODE != 2) {
             if (a.res.p) {
-                float r[COUT];
-                load_row<COUT>(tptr(a.res, g, row), r);
+                float t[COUT];
+                load_row<COUT>(tptr(a.res, g, row[r]), t);
 #pragma unroll
-                for (int co = 0; co < COUT; ++co) acc[co] += r[co];
+                for (int co = 0; co < COUT; ++co) o[co] += t[co];
             }
             if (a.accum) {
-                float r[COUT];
-                load_row<COUT>(tptr(a.y, g, row), r);
+                float t[COUT];
+                load_row<COUT>(tptr(a.y, g, row[r]), t);
 #pragma unroll
-                for (int co = 0; co < COUT; ++co) acc[co] += r[co];
+                for (int co = 0; co < COUT; ++co) o[co] += t[co];
             }
             if (a.relu) {
 #pragma unroll
-                for (int co = 0; co < COUT; ++co) acc[co] = fmaxf(acc[co], 0.f);
+                for (int co = 0; co < COUT; ++co) o[co] = fmaxf(o[co], 0.f);
             }
             if (a.rmask.p) {
-                float r[COUT];
-                load_row<COUT>(tptr(a.rmask, g, row), r);
+                float t[COUT];
+                load_row<COUT>(tptr(a.rmask, g, row[r]), t);
 #pragma unroll
-                for (int co = 0; co < COUT; ++co) acc[co] = r[co] > 0.f ? acc[co] : 0.f;
+                for (int co = 0; co < COUT; ++co) o[co] = t[co] > 0.f ? o[co] : 0.f;
             }
-            store_row<COUT>(tptr(a.y, g, row), acc);
+            store_row<COUT>(tptr(a.y, g, row[r]), o);
         } else {
-            if (a.y.p) store_row<COUT>(tptr(a.y, g, row), acc);
-            // MLP_k 8 -> 24 -> 1 (models/upsample.py:49-55,156-160), fixed order
+            if (a.y.p) store_row<COUT>(tptr(a.y, g, row[r]), o);
+            // MLP_k 8 -> 24 -> 1 (models/upsample.py:49-55,156-160); hidden units in pairs, inputs in order
             float z = s_head[240];
-#pragma unroll 4
-            for (int j = 0; j < 24; ++j) {
-                float h = s_head[192 + j];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) h = fmaf(s_head[j * 8 + i], acc[i], h);
-                h = fmaxf(h, 0.f);
-                z = fmaf(s_head[216 + j], h, z);
+            for (int j = 0; j < 24; j += 2) {
+                u64 h2 = *reinterpret_cast<const u64 *>(s_head + 192 + j);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) h2 = ffma2(pack2(o[i], o[i]), *reinterpret_cast<const u64 *>(s_head + i * 24 + j), h2);
+                float h0, h1;
+                unpack2(h2, h0, h1);
+                z = fmaf(s_head[216 + j], fmaxf(h0, 0.f), z);
+                z = fmaf(s_head[217 + j], fmaxf(h1, 0.f), z);
             }
             const float p = 1.f / (1.f + expf(-z));
             const int stage = a.stage_base + g;
-            const int64_t o = (stage - a.stage_out_base) * a.out_ld + row;
-            if (a.probs) a.probs[o] = p;
-            if (a.cdf) a.cdf[o] = (uint16_t)(__float2int_rn(__fmul_rn(__fsub_rn(1.f, p), 65534.f)) + 1);
+            const int64_t oi = (stage - a.stage_out_base) * a.out_ld + row[r];
+            if (a.probs) a.probs[oi] = p;
+            if (a.cdf) a.cdf[oi] = (uint16_t)(__float2int_rn(__fmul_rn(__fsub_rn(1.f, p), 65534.f)) + 1);
             if (a.bits_partial || a.dz) {
-                const float y = (float)((a.occ[row] >> stage) & 1u);
-                const float q = __fsub_rn(1.f, p);
+                const float y = (float)((a.occ[row[r]] >> stage) & 1u);
+                const float qv = __fsub_rn(1.f, p);
                 // nn.BCELoss clamps log at -100 (models/model_core.py:14)
-                const float lp = fmaxf(logf(p), -100.f), lq = fmaxf(logf(q), -100.f);
-                bits = -(y * lp + (1.f - y) * lq) * 1.4426950408889634f;
+                const float lp = fmaxf(logf(p), -100.f), lq = fmaxf(logf(qv), -100.f);
+                bits += -(y * lp + (1.f - y) * lq) * 1.4426950408889634f;
                 if (a.dz) {
                     // BCELoss backward (/max((1-p)p, 1e-12)) followed by sigmoid backward (*p(1-p))
-                    const float pq = q * p;
-                    a.dz[o] = (p - y) / fmaxf(pq, 1e-12f) * pq * a.dz_scale;
+                    const float pq = qv * p;
+                    a.dz[oi] = (p - y) / fmaxf(pq, 1e-12f) * pq * a.dz_scale;
                 }
             }
         }
@@ -219,7 +298,11 @@ __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
 
 // ------------------------------------------------------------------------------------------------
 // Weight gradient of the 3x3x3 conv: dW[k][ci][co] = sum_o x[nbr(o,k)][ci] * dy[o][co], db = sum_o dy[o].
-// Block = 27 offsets x 8 row-subsets (+8 bias threads); each thread keeps CIN*COUT sums in registers.
+// Tile-staged: a block walks its row chunk in tiles of BW_T rows.  Stage: the gathered inputs of all 27 offsets
+// (zero rows for absent neighbours) and the dy tile go to shared memory with many independent loads in flight.
+// Compute: thread (split, k, q) keeps dW[k][0..CI-1][2q..2q+1] in registers (packed FFMA2) and walks its share of
+// the tile rows in ascending order.  Partial sums: per thread over its rows, then over the BW row splits, then over
+// the chunks (finalize kernel) -- every order fixed, no floating-point atomics.
 // ------------------------------------------------------------------------------------------------
 struct BwdWArgs {
     RowMap map;
@@ -229,93 +312,112 @@ struct BwdWArgs {
     int cin_base, cin_step;
     float *partial;  // [n_chunks][P]
     int64_t P;
-    int64_t chunk;  // rows per chunk (multiple of 8)
+    int64_t chunk;  // rows per chunk (multiple of BW_T)
 };
 constexpr int BWDW_TPB = 224;
+constexpr int BW_T = 32;  // rows per tile
 
 template <int CIN, int COUT, int MODE>
 __global__ void __launch_bounds__(BWDW_TPB) conv27_bwd_w_kernel(const BwdWArgs a) {
-    constexpr int CI = (MODE == 1) ? 7 : CIN;
+    constexpr int CI = (MODE == 1) ? 8 : CIN;        // staged input width (bit inputs are padded to 8 channels)
+    constexpr int HQ = COUT / 2;                     // co pairs
+    constexpr int NT = 27 * HQ;                      // threads per row split
+    constexpr int TS = 216 / NT;                     // row splits per tile (2 for COUT 8, 4 for COUT 4)
+    constexpr int TPS = BW_T / TS;                   // tile rows per split
+    constexpr int KS = BW_T * CI + 4;                // per-offset stride in floats (+4: conflict-free LDS.128 across offsets)
+    static_assert(NT * TS == 216 && TPS * TS == BW_T, "thread mapping");
+    __shared__ __align__(16) float s_x[27 * KS];
+    __shared__ __align__(16) float s_dy[BW_T * COUT];
     const int g = blockIdx.y;
     const int cin = (MODE == 1) ? (a.cin_base + g * a.cin_step) : CIN;
     const int tid = threadIdx.x;
     const int64_t r0 = blockIdx.x * a.chunk;
     const int64_t r1 = min(r0 + a.chunk, a.map.n_rows);
     float *out = a.partial + blockIdx.x * a.P;
-    if (tid < 216) {
-        const int k = tid >> 3, sub = tid & 7;
-        const int c = k % 9, j = k / 9;
-        float acc[CI * COUT];
+
+    const bool is_mm = tid < 216;
+    const int ts = tid / NT, kq = tid % NT, k = kq / HQ, q = kq % HQ;
+    u64 acc[CI];
 #pragma unroll
-        for (int i = 0; i < CI * COUT; ++i) acc[i] = 0.f;
-        for (int64_t r = r0 + sub; r < r1; r += 8) {
-            const uint32_t m3 = (a.map.mask[r] >> (3 * c)) & 7u;
-            if (!((m3 >> j) & 1u)) continue;
-            const int nb = a.map.anchor[c * a.map.ld + r] + __popc(m3 & ((1u << j) - 1u));
-            float dyv[COUT];
-            load_row<COUT>(tptr(a.dy, g, r), dyv);
-            if (MODE == 1) {
-                const unsigned o = a.occ[nb];
+    for (int i = 0; i < CI; ++i) acc[i] = 0ull;
+    float bsum = 0.f;
+
+    for (int64_t t0 = r0; t0 < r1; t0 += BW_T) {
+        // ---- stage: task = (tile row t, neighbour column c): up to three consecutive input rows
+        for (int task = tid; task < BW_T * 9; task += BWDW_TPB) {
+            const int c = task / BW_T, t = task % BW_T;
+            const int64_t r = t0 + t;
+            uint32_t m3 = 0;
+            int nb = 0;
+            if (r < r1) {
+                m3 = (a.map.mask[r] >> (3 * c)) & 7u;
+                if (m3) nb = a.map.anchor[c * a.map.ld + r];
+            }
 #pragma unroll
-                for (int ci = 0; ci < CI; ++ci) {
-                    const float xb = (ci < cin && ((o >> ci) & 1u)) ? 1.f : 0.f;
+            for (int j = 0; j < 3; ++j) {
+                float v[CI];
 #pragma unroll
-                    for (int co = 0; co < COUT; ++co) acc[ci * COUT + co] = fmaf(xb, dyv[co], acc[ci * COUT + co]);
+                for (int i = 0; i < CI; ++i) v[i] = 0.f;
+                if ((m3 >> j) & 1u) {
+                    if (MODE == 1) {
+                        const unsigned o = a.occ[nb];
+#pragma unroll
+                        for (int i = 0; i < 7; ++i) v[i] = (i < cin && ((o >> i) & 1u)) ? 1.f : 0.f;
+                    } else {
+                        load_row<CIN>(tptr(a.x, g, nb), v);
+                    }
+                    ++nb;
                 }
-            } else {
-                float xv[CIN];
-                load_row<CIN>(tptr(a.x, g, nb), xv);
-#pragma unroll
-                for (int ci = 0; ci < CIN; ++ci) {
-#pragma unroll
-                    for (int co = 0; co < COUT; ++co) acc[ci * COUT + co] = fmaf(xv[ci], dyv[co], acc[ci * COUT + co]);
-                }
+                store_row<CI>(s_x + (c + 9 * j) * KS + t * CI, v);
             }
         }
-        // 8 subsets live in 8 adjacent lanes: fixed xor tree.  Warp 6 holds only 24 conv lanes (the
-        // other 8 lanes are the bias threads below), so its shuffle mask is narrower.
-        const unsigned wmask = tid >= 192 ? 0x00ffffffu : 0xffffffffu;
-#pragma unroll
-        for (int i = 0; i < CI * COUT; ++i) {
-            float v = acc[i];
-            v += __shfl_xor_sync(wmask, v, 1);
-            v += __shfl_xor_sync(wmask, v, 2);
-            v += __shfl_xor_sync(wmask, v, 4);
-            acc[i] = v;
+        for (int i = tid; i < BW_T * COUT / 4; i += BWDW_TPB) {
+            const int t = i / (COUT / 4), part = i % (COUT / 4);
+            const int64_t r = t0 + t;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < r1) v = *reinterpret_cast<const float4 *>(tptr(a.dy, g, r) + 4 * part);
+            *reinterpret_cast<float4 *>(s_dy + t * COUT + 4 * part) = v;
         }
-        if (sub == 0) {
-            float *w = out + a.w_off[g] + k * cin * COUT;
+        __syncthreads();
+        // ---- compute
+        if (is_mm) {
+            const float *xs = s_x + k * KS + ts * TPS * CI;
+            const float *ds = s_dy + ts * TPS * COUT + 2 * q;
+#pragma unroll 4
+            for (int t = 0; t < TPS; ++t) {
+                float xv[CI];
+                load_row<CI>(xs + t * CI, xv);
+                const u64 d2 = *reinterpret_cast<const u64 *>(ds + t * COUT);
 #pragma unroll
-            for (int ci = 0; ci < CI; ++ci) {
-                if (ci < cin) {
-#pragma unroll
-                    for (int co = 0; co < COUT; ++co) w[ci * COUT + co] = acc[ci * COUT + co];
-                }
+                for (int i = 0; i < CI; ++i) acc[i] = ffma2(pack2(xv[i], xv[i]), d2, acc[i]);
             }
+        } else if (tid - 216 < COUT) {
+#pragma unroll 8
+            for (int t = 0; t < BW_T; ++t) bsum += s_dy[t * COUT + (tid - 216)];
         }
-    } else {
-        const int sub = tid - 216;
-        float acc[COUT];
+        __syncthreads();
+    }
+    // ---- combine the row splits in order, write this chunk's partial
+    float *s_part = s_x;  // [TS][NT][CI][2]
+    if (is_mm) {
 #pragma unroll
-        for (int i = 0; i < COUT; ++i) acc[i] = 0.f;
-        for (int64_t r = r0 + sub; r < r1; r += 8) {
-            float dyv[COUT];
-            load_row<COUT>(tptr(a.dy, g, r), dyv);
+        for (int i = 0; i < CI; ++i) *reinterpret_cast<u64 *>(s_part + ((ts * NT + kq) * CI + i) * 2) = acc[i];
+    }
+    __syncthreads();
+    if (tid < NT) {
+        float *w = out + a.w_off[g] + k * cin * COUT + 2 * q;
 #pragma unroll
-            for (int co = 0; co < COUT; ++co) acc[co] += dyv[co];
+        for (int i = 0; i < CI; ++i) {
+            float lo = 0.f, hi = 0.f;
+#pragma unroll
+            for (int sidx = 0; sidx < TS; ++sidx) {
+                lo += s_part[((sidx * NT + kq) * CI + i) * 2];
+                hi += s_part[((sidx * NT + kq) * CI + i) * 2 + 1];
+            }
+            if (i < cin) w[i * COUT] = lo, w[i * COUT + 1] = hi;
         }
-#pragma unroll
-        for (int i = 0; i < COUT; ++i) {
-            float v = acc[i];
-            v += __shfl_xor_sync(0xff000000u, v, 1);
-            v += __shfl_xor_sync(0xff000000u, v, 2);
-            v += __shfl_xor_sync(0xff000000u, v, 4);
-            acc[i] = v;
-        }
-        if (sub == 0 && a.b_off[g] >= 0) {
-#pragma unroll
-            for (int co = 0; co < COUT; ++co) out[a.b_off[g] + co] = acc[co];
-        }
+    } else if (tid >= 216 && tid - 216 < COUT && a.b_off[g] >= 0) {
+        out[a.b_off[g] + (tid - 216)] = bsum;
     }
 }
 
