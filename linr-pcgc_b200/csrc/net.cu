@@ -171,7 +171,7 @@ struct NetWs {
 
 int chunks_for(int64_t R) {
     int64_t nb = ceil_div64(R, 64);
-    int64_t cap = 2 * (int64_t)linr_sm_count();
+    int64_t cap = 4 * (int64_t)linr_sm_count();  // weight-gradient partial sums: one per row chunk
     if (nb > cap) nb = cap;
     if (nb < 1) nb = 1;
     return (int)nb;
@@ -321,7 +321,13 @@ void launch_bwd_w(const RowMap &m, const NetWs &w, int P, const int *w_off, cons
     dim3 grid((unsigned)w.n_chunks, (unsigned)G);
     constexpr int cls = MODE == 1 ? K_BWDWBITS : (COUT == 8 ? K_BWDW88 : (CIN == 8 ? K_BWDW84 : K_BWDW44));
     ProfScope prof(cls, m.n_rows * G, s);
-    conv27_bwd_w_kernel<CIN, COUT, MODE><<<grid, BWDW_TPB, 0, s>>>(a);
+    using Cfg = BwdWCfg<CIN, COUT, MODE>;
+    static bool attr_set = false;  // > 48 KB of dynamic shared memory needs the opt-in once per kernel
+    if (!attr_set) {
+        cudaFuncSetAttribute(conv27_bwd_w_kernel<CIN, COUT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+        attr_set = true;
+    }
+    conv27_bwd_w_kernel<CIN, COUT, MODE><<<grid, BWDW_TPB, Cfg::SMEM, s>>>(a);
 }
 template <int CIN, int COUT>
 void launch_pw_bwd_w(int64_t R, const NetWs &w, int P, const int *w_off, const int *b_off, int G, Tens x, Tens dy, cudaStream_t s) {

@@ -89,6 +89,10 @@ __device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
+// in-place forms: "acc = fma(a, b, acc)" with the accumulator as a read-write operand, so that a predicated use
+// compiles to one predicated FFMA2 (a separate destination costs two predicated moves per instruction)
+__device__ __forceinline__ void ffma2_acc(u64 &acc, u64 a, u64 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+__device__ __forceinline__ void fadd2_acc(u64 &acc, u64 b) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(b)); }
 __device__ __forceinline__ u64 fadd2(u64 a, u64 b) {
     u64 d;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -159,58 +163,41 @@ __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
         for (int j = 0; j < 3; ++j) {
             if (!((any >> j) & 1u)) continue;
             const float *wk = s_w + (c + 9 * j) * cin * COUT;
-            bool on[CONV_RPT];
+            // A row without this neighbour multiplies by zero instead of branching: acc + 0*w == acc bit for bit
+            // (acc is never -0: it starts at +0 and x*w + acc rounds an exact zero to +0), so the result does not
+            // depend on which rows share a thread -- encoder and decoder batches stay bit-identical.
             float xv[CONV_RPT][CIN];
-            unsigned ob[CONV_RPT];
 #pragma unroll
             for (int r = 0; r < CONV_RPT; ++r) {
-                on[r] = (m3[r] >> j) & 1u;
-                ob[r] = 0;
-                if (on[r]) {
-                    if (MODE == 1) ob[r] = a.occ[nb[r]];
-                    else load_row<CIN>(tptr(a.x, g, nb[r]), xv[r]);
+                const bool on = (m3[r] >> j) & 1u;
+#pragma unroll
+                for (int i = 0; i < CIN; ++i) xv[r][i] = 0.f;
+                if (on) {
+                    if (MODE == 1) {
+                        const unsigned o = a.occ[nb[r]];
+#pragma unroll
+                        for (int i = 0; i < 7; ++i) xv[r][i] = ((o >> i) & 1u) ? 1.f : 0.f;
+                    } else {
+                        load_row<CIN>(tptr(a.x, g, nb[r]), xv[r]);
+                    }
                     ++nb[r];
                 }
             }
-            if (MODE == 1) {
-                // input channel ci = bit ci of the neighbour's occupancy byte ({0,1}): acc += w (same rounding as fma(1,w,acc))
 #pragma unroll
-                for (int ci = 0; ci < 7; ++ci) {
-                    if (ci < cin) {
-                        const ulonglong2 *w2 = reinterpret_cast<const ulonglong2 *>(wk + ci * COUT);
-                        u64 wq[HQ];
+            for (int ci = 0; ci < CIN; ++ci) {
+                if (MODE == 1 && ci >= cin) break;
+                const ulonglong2 *w2 = reinterpret_cast<const ulonglong2 *>(wk + ci * COUT);
+                u64 wq[HQ];
 #pragma unroll
-                        for (int q = 0; q < HQ; q += 2) {
-                            const ulonglong2 t = w2[q >> 1];
-                            wq[q] = t.x, wq[q + 1] = t.y;
-                        }
-#pragma unroll
-                        for (int r = 0; r < CONV_RPT; ++r) {
-                            if (on[r] && ((ob[r] >> ci) & 1u)) {
-#pragma unroll
-                                for (int q = 0; q < HQ; ++q) acc[r][q] = fadd2(acc[r][q], wq[q]);
-                            }
-                        }
-                    }
+                for (int q = 0; q < HQ; q += 2) {
+                    const ulonglong2 t = w2[q >> 1];
+                    wq[q] = t.x, wq[q + 1] = t.y;
                 }
-            } else {
 #pragma unroll
-                for (int ci = 0; ci < CIN; ++ci) {
-                    const ulonglong2 *w2 = reinterpret_cast<const ulonglong2 *>(wk + ci * COUT);
-                    u64 wq[HQ];
+                for (int r = 0; r < CONV_RPT; ++r) {
+                    const u64 xx = pack2(xv[r][ci], xv[r][ci]);
 #pragma unroll
-                    for (int q = 0; q < HQ; q += 2) {
-                        const ulonglong2 t = w2[q >> 1];
-                        wq[q] = t.x, wq[q + 1] = t.y;
-                    }
-#pragma unroll
-                    for (int r = 0; r < CONV_RPT; ++r) {
-                        if (on[r]) {
-                            const u64 xx = pack2(xv[r][ci], xv[r][ci]);
-#pragma unroll
-                            for (int q = 0; q < HQ; ++q) acc[r][q] = ffma2(xx, wq[q], acc[r][q]);
-                        }
-                    }
+                    for (int q = 0; q < HQ; ++q) ffma2_acc(acc[r][q], xx, wq[q]);
                 }
             }
         }
@@ -225,7 +212,7 @@ __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
         for (int q = 0; q < HQ; ++q) unpack2(acc[r][q], o[2 * q], o[2 * q + 1]);
 #pragma unroll
         for (int co = 0; co < COUT; ++co) o[co] += s_b[co];
-        if (MODE != 2) {
+        if constexpr (MODE != 2) {
             if (a.res.p) {
                 float t[COUT];
                 load_row<COUT>(tptr(a.res, g, row[r]), t);
@@ -257,7 +244,7 @@ __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
             for (int j = 0; j < 24; j += 2) {
                 u64 h2 = *reinterpret_cast<const u64 *>(s_head + 192 + j);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) h2 = ffma2(pack2(o[i], o[i]), *reinterpret_cast<const u64 *>(s_head + i * 24 + j), h2);
+                for (int i = 0; i < 8; ++i) ffma2_acc(h2, pack2(o[i], o[i]), *reinterpret_cast<const u64 *>(s_head + i * 24 + j));
                 float h0, h1;
                 unpack2(h2, h0, h1);
                 z = fmaf(s_head[216 + j], fmaxf(h0, 0.f), z);
@@ -317,17 +304,33 @@ struct BwdWArgs {
 constexpr int BWDW_TPB = 224;
 constexpr int BW_T = 32;  // rows per tile
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");  // src_bytes 0: zero fill
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int CIN, int COUT, int MODE>
+struct BwdWCfg {
+    static constexpr int CI = (MODE == 1) ? 8 : CIN;   // staged input width (bit inputs are padded to 8 channels)
+    static constexpr int HQ = COUT / 2;                // co pairs
+    static constexpr int NT = 27 * HQ;                 // threads per row split
+    static constexpr int TS = 216 / NT;                // row splits per tile (2 for COUT 8, 4 for COUT 4)
+    static constexpr int TPS = BW_T / TS;              // tile rows per split
+    static constexpr int KS = BW_T * CI + 4;           // per-offset stride in floats (+4: conflict-free LDS.128 across offsets)
+    static constexpr int NBUF = (MODE == 1) ? 1 : 2;   // float inputs: cp.async double buffer
+    static constexpr int BUF = 27 * KS + BW_T * COUT;  // floats per buffer: gathered inputs, then the dy tile
+    static constexpr size_t SMEM = (size_t)NBUF * BUF * sizeof(float);
+};
+
 template <int CIN, int COUT, int MODE>
 __global__ void __launch_bounds__(BWDW_TPB) conv27_bwd_w_kernel(const BwdWArgs a) {
-    constexpr int CI = (MODE == 1) ? 8 : CIN;        // staged input width (bit inputs are padded to 8 channels)
-    constexpr int HQ = COUT / 2;                     // co pairs
-    constexpr int NT = 27 * HQ;                      // threads per row split
-    constexpr int TS = 216 / NT;                     // row splits per tile (2 for COUT 8, 4 for COUT 4)
-    constexpr int TPS = BW_T / TS;                   // tile rows per split
-    constexpr int KS = BW_T * CI + 4;                // per-offset stride in floats (+4: conflict-free LDS.128 across offsets)
+    using Cfg = BwdWCfg<CIN, COUT, MODE>;
+    constexpr int CI = Cfg::CI, HQ = Cfg::HQ, NT = Cfg::NT, TS = Cfg::TS, TPS = Cfg::TPS, KS = Cfg::KS, BUF = Cfg::BUF;
+    constexpr int HV = CI / 4;  // 16-byte pieces per input row
     static_assert(NT * TS == 216 && TPS * TS == BW_T, "thread mapping");
-    __shared__ __align__(16) float s_x[27 * KS];
-    __shared__ __align__(16) float s_dy[BW_T * COUT];
+    extern __shared__ __align__(16) float s_buf[];
     const int g = blockIdx.y;
     const int cin = (MODE == 1) ? (a.cin_base + g * a.cin_step) : CIN;
     const int tid = threadIdx.x;
@@ -342,10 +345,10 @@ __global__ void __launch_bounds__(BWDW_TPB) conv27_bwd_w_kernel(const BwdWArgs a
     for (int i = 0; i < CI; ++i) acc[i] = 0ull;
     float bsum = 0.f;
 
-    for (int64_t t0 = r0; t0 < r1; t0 += BW_T) {
-        // ---- stage: task = (tile row t, neighbour column c): up to three consecutive input rows
-        for (int task = tid; task < BW_T * 9; task += BWDW_TPB) {
-            const int c = task / BW_T, t = task % BW_T;
+    // Stage one tile: piece = (neighbour column c, tile row t, 16-byte part h); adjacent lanes write adjacent 16 B.
+    auto stage = [&](int64_t t0, float *buf) {
+        for (int task = tid; task < 9 * BW_T * HV; task += BWDW_TPB) {
+            const int h = task % HV, t = (task / HV) % BW_T, c = task / (HV * BW_T);
             const int64_t r = t0 + t;
             uint32_t m3 = 0;
             int nb = 0;
@@ -355,50 +358,85 @@ __global__ void __launch_bounds__(BWDW_TPB) conv27_bwd_w_kernel(const BwdWArgs a
             }
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-                float v[CI];
-#pragma unroll
-                for (int i = 0; i < CI; ++i) v[i] = 0.f;
-                if ((m3 >> j) & 1u) {
-                    if (MODE == 1) {
-                        const unsigned o = a.occ[nb];
-#pragma unroll
-                        for (int i = 0; i < 7; ++i) v[i] = (i < cin && ((o >> i) & 1u)) ? 1.f : 0.f;
-                    } else {
-                        load_row<CIN>(tptr(a.x, g, nb), v);
+                const bool on = (m3 >> j) & 1u;
+                float *dst = buf + (c + 9 * j) * KS + t * CI + 4 * h;
+                if (MODE == 1) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (on) {
+                        const unsigned o = a.occ[nb] >> (4 * h);
+                        const int lim = cin - 4 * h;  // channels >= cin do not exist
+                        v.x = (lim > 0 && (o & 1u)) ? 1.f : 0.f;
+                        v.y = (lim > 1 && (o & 2u)) ? 1.f : 0.f;
+                        v.z = (lim > 2 && (o & 4u)) ? 1.f : 0.f;
+                        v.w = (lim > 3 && (o & 8u)) ? 1.f : 0.f;
                     }
-                    ++nb;
+                    *reinterpret_cast<float4 *>(dst) = v;
+                } else {
+                    cp_async16(dst, on ? (const void *)(tptr(a.x, g, nb) + 4 * h) : (const void *)a.x.p, on ? 16 : 0);
                 }
-                store_row<CI>(s_x + (c + 9 * j) * KS + t * CI, v);
+                nb += on ? 1 : 0;
             }
         }
+        float *dyb = buf + 27 * KS;
         for (int i = tid; i < BW_T * COUT / 4; i += BWDW_TPB) {
             const int t = i / (COUT / 4), part = i % (COUT / 4);
             const int64_t r = t0 + t;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < r1) v = *reinterpret_cast<const float4 *>(tptr(a.dy, g, r) + 4 * part);
-            *reinterpret_cast<float4 *>(s_dy + t * COUT + 4 * part) = v;
+            if (MODE == 1) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < r1) v = *reinterpret_cast<const float4 *>(tptr(a.dy, g, r) + 4 * part);
+                *reinterpret_cast<float4 *>(dyb + t * COUT + 4 * part) = v;
+            } else {
+                const bool in = r < r1;
+                cp_async16(dyb + t * COUT + 4 * part, in ? (const void *)(tptr(a.dy, g, r) + 4 * part) : (const void *)a.dy.p, in ? 16 : 0);
+            }
         }
-        __syncthreads();
-        // ---- compute
+    };
+    auto compute = [&](const float *buf) {
         if (is_mm) {
-            const float *xs = s_x + k * KS + ts * TPS * CI;
-            const float *ds = s_dy + ts * TPS * COUT + 2 * q;
+            const float *xs = buf + k * KS + ts * TPS * CI;
+            const float *ds = buf + 27 * KS + ts * TPS * COUT + 2 * q;
 #pragma unroll 4
             for (int t = 0; t < TPS; ++t) {
                 float xv[CI];
                 load_row<CI>(xs + t * CI, xv);
                 const u64 d2 = *reinterpret_cast<const u64 *>(ds + t * COUT);
 #pragma unroll
-                for (int i = 0; i < CI; ++i) acc[i] = ffma2(pack2(xv[i], xv[i]), d2, acc[i]);
+                for (int i = 0; i < CI; ++i) ffma2_acc(acc[i], pack2(xv[i], xv[i]), d2);
             }
         } else if (tid - 216 < COUT) {
+            const float *ds = buf + 27 * KS + (tid - 216);
 #pragma unroll 8
-            for (int t = 0; t < BW_T; ++t) bsum += s_dy[t * COUT + (tid - 216)];
+            for (int t = 0; t < BW_T; ++t) bsum += ds[t * COUT];
+        }
+    };
+
+    if (MODE == 1) {
+        for (int64_t t0 = r0; t0 < r1; t0 += BW_T) {
+            stage(t0, s_buf);
+            __syncthreads();
+            compute(s_buf);
+            __syncthreads();
+        }
+    } else {
+        // double buffer: the gathers of tile i+1 are in flight (cp.async) while tile i is multiplied
+        if (r0 < r1) {
+            stage(r0, s_buf);
+            cp_async_commit();
+        }
+        int it = 0;
+        for (int64_t t0 = r0; t0 < r1; t0 += BW_T, ++it) {
+            cp_async_wait_all();
+            __syncthreads();  // tile `it` is visible to everyone; everyone is done with the other buffer
+            if (t0 + BW_T < r1) {
+                stage(t0 + BW_T, s_buf + ((it + 1) & 1) * BUF);
+                cp_async_commit();
+            }
+            compute(s_buf + (it & 1) * BUF);
         }
         __syncthreads();
     }
     // ---- combine the row splits in order, write this chunk's partial
-    float *s_part = s_x;  // [TS][NT][CI][2]
+    float *s_part = s_buf;  // [TS][NT][CI][2]
     if (is_mm) {
 #pragma unroll
         for (int i = 0; i < CI; ++i) *reinterpret_cast<u64 *>(s_part + ((ts * NT + kq) * CI + i) * 2) = acc[i];
