@@ -192,7 +192,7 @@ NetWs carve_net(void *ws, size_t bytes, int64_t R, int train, int P, int S) {
     w.ob_t2 = c.take<float>(r * 28), w.ob_z = c.take<float>(r * 56);
     w.hc = c.take<float>(r * 64);
     w.dzs = c.take<float>(r * 8);
-    w.bits_partial = c.take<float>((size_t)ceil_div64(r, CONV_ROWS) * 8);
+    w.bits_partial = c.take<float>((size_t)ceil_div64(r, (ConvCfg<8, 8, 2>::ROWS)) * 8);
     if (train) {
         w.dc = c.take<float>(r * 64), w.dhh = c.take<float>(r * 64), w.dg = c.take<float>(r * 8);
         w.g_dz = c.take<float>(r * 56), w.g_dt0 = c.take<float>(r * 28), w.g_dy = c.take<float>(r * 56);
@@ -215,7 +215,7 @@ RowMap map_of(const linr_rows *r) { return RowMap{r->d_anchor, r->ld, r->d_mask,
 template <int CIN, int COUT, int MODE>
 void launch_conv(const ConvArgs &a, int G, cudaStream_t s) {
     if (a.map.n_rows <= 0) return;
-    dim3 grid((unsigned)ceil_div64(a.map.n_rows, CONV_ROWS), (unsigned)G);
+    dim3 grid((unsigned)ceil_div64(a.map.n_rows, (ConvCfg<CIN, COUT, MODE>::ROWS)), (unsigned)G);
     constexpr int cls = MODE == 2 ? K_CONVHEAD : MODE == 1 ? K_CONVBITS : (CIN == 8 ? (COUT == 8 ? K_CONV88 : K_CONV84) : (COUT == 8 ? K_CONV48 : K_CONV44));
     ProfScope prof(cls, a.map.n_rows * G, s);
     conv27_kernel<CIN, COUT, MODE><<<grid, CONV_TPB, 0, s>>>(a);
@@ -540,7 +540,7 @@ int linr_net_forward(const float *d_params, int scale_num, const linr_rows *rows
                  train ? w.dzs : nullptr, loss_scale * 1.4426950408889634f, want_bits ? w.bits_partial : nullptr, 0, s);
     if (d_bits) {
         ProfScope prof(K_REDUCE, 1, s);
-        bits_finalize_kernel<<<1, 256, 0, s>>>(w.bits_partial, (int)ceil_div64(R, CONV_ROWS) * 8, d_bits);
+        bits_finalize_kernel<<<1, 256, 0, s>>>(w.bits_partial, (int)ceil_div64(R, (ConvCfg<8, 8, 2>::ROWS)) * 8, d_bits);
     }
     LINR_LAUNCH_CHECK();
     return LINR_OK;

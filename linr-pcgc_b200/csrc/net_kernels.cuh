@@ -37,6 +37,19 @@ __device__ __forceinline__ void load_row(const float *p, float (&v)[C]) {
         v[i] = q.x, v[i + 1] = q.y, v[i + 2] = q.z, v[i + 3] = q.w;
     }
 }
+// Gathered feature rows (read-only in the kernel that gathers them): one 256-bit load per 8-channel row
+// (LDG.E.256 on sm_100a) halves the L1 wavefronts of two strided 128-bit loads.
+template <int C>
+__device__ __forceinline__ void gather_row(const float *p, float (&v)[C]) {
+    if constexpr (C == 8) {
+        asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                     : "l"(p));
+    } else {
+        const float4 q = __ldg(reinterpret_cast<const float4 *>(p));
+        v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
+    }
+}
 template <int C>
 __device__ __forceinline__ void store_row(float *p, const float (&v)[C]) {
 #pragma unroll
@@ -72,8 +85,13 @@ struct ConvArgs {
 };
 
 constexpr int CONV_TPB = 128;
-constexpr int CONV_RPT = 2;                       // rows per thread (weights read from shared memory once for both)
-constexpr int CONV_ROWS = CONV_TPB * CONV_RPT;    // rows per block
+// rows per thread: the weights of an offset are read from shared memory once for all of them (the L1/shared
+// wavefront pipe, not the FMA pipe, is what saturates first)
+template <int CIN, int COUT, int MODE>
+struct ConvCfg {
+    static constexpr int RPT = (CIN == 8 && COUT == 8 && MODE != 1) ? 4 : 2;
+    static constexpr int ROWS = CONV_TPB * RPT;  // rows per block
+};
 
 // Packed fp32x2 FMA (Blackwell FFMA2): two independent IEEE fp32 FMAs per instruction, so results are bit-identical
 // to scalar fmaf; `pack2(x, x)` compiles to the scalar-broadcast operand form (no extra moves).
@@ -103,6 +121,7 @@ template <int CIN, int COUT, int MODE>
 __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
     constexpr int WMAX = (MODE == 1) ? 27 * 7 * COUT : 27 * CIN * COUT;
     constexpr int HQ = COUT / 2;  // accumulator pairs per row
+    constexpr int CONV_RPT = ConvCfg<CIN, COUT, MODE>::RPT, CONV_ROWS = ConvCfg<CIN, COUT, MODE>::ROWS;
     __shared__ __align__(16) float s_w[WMAX];
     __shared__ float s_b[COUT];
     // head (MODE 2): W1 transposed [8][24] so that hidden-unit pairs are adjacent, then b1[24], w2[24], b2
@@ -178,7 +197,7 @@ __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
 #pragma unroll
                         for (int i = 0; i < 7; ++i) xv[r][i] = ((o >> i) & 1u) ? 1.f : 0.f;
                     } else {
-                        load_row<CIN>(tptr(a.x, g, nb[r]), xv[r]);
+                        gather_row<CIN>(tptr(a.x, g, nb[r]), xv[r]);
                     }
                     ++nb[r];
                 }
@@ -302,35 +321,34 @@ struct BwdWArgs {
     int64_t chunk;  // rows per chunk (multiple of BW_T)
 };
 constexpr int BWDW_TPB = 224;
-constexpr int BW_T = 32;  // rows per tile
-
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, int src_bytes) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");  // src_bytes 0: zero fill
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+constexpr int BW_T = 128;  // rows per tile
 
 template <int CIN, int COUT, int MODE>
 struct BwdWCfg {
-    static constexpr int CI = (MODE == 1) ? 8 : CIN;   // staged input width (bit inputs are padded to 8 channels)
-    static constexpr int HQ = COUT / 2;                // co pairs
-    static constexpr int NT = 27 * HQ;                 // threads per row split
-    static constexpr int TS = 216 / NT;                // row splits per tile (2 for COUT 8, 4 for COUT 4)
+    static constexpr int CI = (MODE == 1) ? 8 : CIN;   // accumulated input width (bit inputs: up to 7 of 8 used)
+    static constexpr int QT = COUT / 4;                // threads per offset, each owning 4 output channels (2 packed pairs)
+    static constexpr int NT = 27 * QT;                 // threads per row split
+    static constexpr int TS = 216 / NT;                // row splits per tile (4 for COUT 8, 8 for COUT 4)
     static constexpr int TPS = BW_T / TS;              // tile rows per split
-    static constexpr int KS = BW_T * CI + 4;           // per-offset stride in floats (+4: conflict-free LDS.128 across offsets)
-    static constexpr int NBUF = (MODE == 1) ? 1 : 2;   // float inputs: cp.async double buffer
-    static constexpr int BUF = 27 * KS + BW_T * COUT;  // floats per buffer: gathered inputs, then the dy tile
-    static constexpr size_t SMEM = (size_t)NBUF * BUF * sizeof(float);
+    static constexpr int STAGE = BW_T + BW_T * 9 + BW_T * COUT;  // words: mask, anchors [t][9], dy tile [t][COUT]
+    static constexpr int PART = 216 * CI * 4;          // floats needed to combine the row splits at the end
+    static constexpr int WORDS = STAGE > PART ? STAGE : PART;
+    static constexpr size_t SMEM = (size_t)WORDS * 4;
 };
 
+// Only the kernel-map slice and the dy tile are staged in shared memory (coalesced); the gathered input rows are
+// read straight from global memory / L1 with one 256-bit load per (row, offset) -- staging them costs more L1
+// wavefronts than the multiply itself.  Thread = (row split, offset k, output-channel quad): it walks its rows in
+// ascending order, four gathers in flight, with dW[k][0..CI-1][4q..4q+3] in registers (packed FFMA2).
 template <int CIN, int COUT, int MODE>
 __global__ void __launch_bounds__(BWDW_TPB) conv27_bwd_w_kernel(const BwdWArgs a) {
     using Cfg = BwdWCfg<CIN, COUT, MODE>;
-    constexpr int CI = Cfg::CI, HQ = Cfg::HQ, NT = Cfg::NT, TS = Cfg::TS, TPS = Cfg::TPS, KS = Cfg::KS, BUF = Cfg::BUF;
-    constexpr int HV = CI / 4;  // 16-byte pieces per input row
-    static_assert(NT * TS == 216 && TPS * TS == BW_T, "thread mapping");
+    constexpr int CI = Cfg::CI, QT = Cfg::QT, NT = Cfg::NT, TS = Cfg::TS, TPS = Cfg::TPS;
+    static_assert(NT * TS == 216 && TPS * TS == BW_T && TPS % 4 == 0, "thread mapping");
     extern __shared__ __align__(16) float s_buf[];
+    uint32_t *s_mask = reinterpret_cast<uint32_t *>(s_buf);
+    int *s_anch = reinterpret_cast<int *>(s_buf) + BW_T;
+    float *s_dy = s_buf + BW_T + BW_T * 9;
     const int g = blockIdx.y;
     const int cin = (MODE == 1) ? (a.cin_base + g * a.cin_step) : CIN;
     const int tid = threadIdx.x;
@@ -339,124 +357,84 @@ __global__ void __launch_bounds__(BWDW_TPB) conv27_bwd_w_kernel(const BwdWArgs a
     float *out = a.partial + blockIdx.x * a.P;
 
     const bool is_mm = tid < 216;
-    const int ts = tid / NT, kq = tid % NT, k = kq / HQ, q = kq % HQ;
-    u64 acc[CI];
+    const int ts = tid / NT, kq = tid % NT, k = kq / QT, qd = kq % QT;
+    const int c = k % 9, j = k / 9;
+    const uint32_t jbit = 1u << j, jlow = jbit - 1u;
+    u64 acc[CI][2];  // dW[k][ci][4qd .. 4qd+3] over this thread's rows
 #pragma unroll
-    for (int i = 0; i < CI; ++i) acc[i] = 0ull;
+    for (int i = 0; i < CI; ++i) acc[i][0] = acc[i][1] = 0ull;
     float bsum = 0.f;
 
-    // Stage one tile: piece = (neighbour column c, tile row t, 16-byte part h); adjacent lanes write adjacent 16 B.
-    auto stage = [&](int64_t t0, float *buf) {
-        for (int task = tid; task < 9 * BW_T * HV; task += BWDW_TPB) {
-            const int h = task % HV, t = (task / HV) % BW_T, c = task / (HV * BW_T);
-            const int64_t r = t0 + t;
-            uint32_t m3 = 0;
-            int nb = 0;
-            if (r < r1) {
-                m3 = (a.map.mask[r] >> (3 * c)) & 7u;
-                if (m3) nb = a.map.anchor[c * a.map.ld + r];
-            }
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const bool on = (m3 >> j) & 1u;
-                float *dst = buf + (c + 9 * j) * KS + t * CI + 4 * h;
-                if (MODE == 1) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (on) {
-                        const unsigned o = a.occ[nb] >> (4 * h);
-                        const int lim = cin - 4 * h;  // channels >= cin do not exist
-                        v.x = (lim > 0 && (o & 1u)) ? 1.f : 0.f;
-                        v.y = (lim > 1 && (o & 2u)) ? 1.f : 0.f;
-                        v.z = (lim > 2 && (o & 4u)) ? 1.f : 0.f;
-                        v.w = (lim > 3 && (o & 8u)) ? 1.f : 0.f;
-                    }
-                    *reinterpret_cast<float4 *>(dst) = v;
-                } else {
-                    cp_async16(dst, on ? (const void *)(tptr(a.x, g, nb) + 4 * h) : (const void *)a.x.p, on ? 16 : 0);
-                }
-                nb += on ? 1 : 0;
-            }
+    for (int64_t t0 = r0; t0 < r1; t0 += BW_T) {
+        // ---- stage the map slice and the dy tile (rows past the chunk end: empty mask, zero dy)
+        for (int i = tid; i < BW_T; i += BWDW_TPB) s_mask[i] = (t0 + i < r1) ? a.map.mask[t0 + i] : 0u;
+        for (int i = tid; i < BW_T * 9; i += BWDW_TPB) {
+            const int cc = i / BW_T, t = i % BW_T;
+            s_anch[t * 9 + cc] = (t0 + t < r1) ? a.map.anchor[cc * a.map.ld + t0 + t] : 0;
         }
-        float *dyb = buf + 27 * KS;
         for (int i = tid; i < BW_T * COUT / 4; i += BWDW_TPB) {
             const int t = i / (COUT / 4), part = i % (COUT / 4);
-            const int64_t r = t0 + t;
-            if (MODE == 1) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r < r1) v = *reinterpret_cast<const float4 *>(tptr(a.dy, g, r) + 4 * part);
-                *reinterpret_cast<float4 *>(dyb + t * COUT + 4 * part) = v;
-            } else {
-                const bool in = r < r1;
-                cp_async16(dyb + t * COUT + 4 * part, in ? (const void *)(tptr(a.dy, g, r) + 4 * part) : (const void *)a.dy.p, in ? 16 : 0);
-            }
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t0 + t < r1) v = *reinterpret_cast<const float4 *>(tptr(a.dy, g, t0 + t) + 4 * part);
+            *reinterpret_cast<float4 *>(s_dy + t * COUT + 4 * part) = v;
         }
-    };
-    auto compute = [&](const float *buf) {
+        __syncthreads();
         if (is_mm) {
-            const float *xs = buf + k * KS + ts * TPS * CI;
-            const float *ds = buf + 27 * KS + ts * TPS * COUT + 2 * q;
-#pragma unroll 4
-            for (int t = 0; t < TPS; ++t) {
-                float xv[CI];
-                load_row<CI>(xs + t * CI, xv);
-                const u64 d2 = *reinterpret_cast<const u64 *>(ds + t * COUT);
+            const int tb = ts * TPS;
+#pragma unroll 1
+            for (int tt = 0; tt < TPS; tt += 4) {
+                float xv[4][CI];
 #pragma unroll
-                for (int i = 0; i < CI; ++i) ffma2_acc(acc[i], pack2(xv[i], xv[i]), d2);
+                for (int u = 0; u < 4; ++u) {
+                    const int t = tb + tt + u;
+                    const uint32_t m3 = (s_mask[t] >> (3 * c)) & 7u;
+#pragma unroll
+                    for (int i = 0; i < CI; ++i) xv[u][i] = 0.f;
+                    if (m3 & jbit) {
+                        const int nb = s_anch[t * 9 + c] + __popc(m3 & jlow);
+                        if (MODE == 1) {
+                            const unsigned o = a.occ[nb];
+#pragma unroll
+                            for (int i = 0; i < 7; ++i) xv[u][i] = ((o >> i) & 1u) ? 1.f : 0.f;  // channels >= cin are never written out
+                        } else {
+                            gather_row<CIN>(tptr(a.x, g, nb), xv[u]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const ulonglong2 d = *reinterpret_cast<const ulonglong2 *>(s_dy + (tb + tt + u) * COUT + 4 * qd);
+#pragma unroll
+                    for (int i = 0; i < CI; ++i) {
+                        const u64 xx = pack2(xv[u][i], xv[u][i]);
+                        ffma2_acc(acc[i][0], xx, d.x);
+                        ffma2_acc(acc[i][1], xx, d.y);
+                    }
+                }
             }
         } else if (tid - 216 < COUT) {
-            const float *ds = buf + 27 * KS + (tid - 216);
+            const float *ds = s_dy + (tid - 216);
 #pragma unroll 8
             for (int t = 0; t < BW_T; ++t) bsum += ds[t * COUT];
         }
-    };
-
-    if (MODE == 1) {
-        for (int64_t t0 = r0; t0 < r1; t0 += BW_T) {
-            stage(t0, s_buf);
-            __syncthreads();
-            compute(s_buf);
-            __syncthreads();
-        }
-    } else {
-        // double buffer: the gathers of tile i+1 are in flight (cp.async) while tile i is multiplied
-        if (r0 < r1) {
-            stage(r0, s_buf);
-            cp_async_commit();
-        }
-        int it = 0;
-        for (int64_t t0 = r0; t0 < r1; t0 += BW_T, ++it) {
-            cp_async_wait_all();
-            __syncthreads();  // tile `it` is visible to everyone; everyone is done with the other buffer
-            if (t0 + BW_T < r1) {
-                stage(t0 + BW_T, s_buf + ((it + 1) & 1) * BUF);
-                cp_async_commit();
-            }
-            compute(s_buf + (it & 1) * BUF);
-        }
         __syncthreads();
     }
-    // ---- combine the row splits in order, write this chunk's partial
-    float *s_part = s_buf;  // [TS][NT][CI][2]
+    // ---- combine the row splits in order, write this chunk's partial: s_part[ts][k][ci][co]
+    float *s_part = s_buf;
     if (is_mm) {
 #pragma unroll
-        for (int i = 0; i < CI; ++i) *reinterpret_cast<u64 *>(s_part + ((ts * NT + kq) * CI + i) * 2) = acc[i];
+        for (int i = 0; i < CI; ++i)
+            *reinterpret_cast<ulonglong2 *>(s_part + ((ts * 27 + k) * CI + i) * COUT + 4 * qd) = make_ulonglong2(acc[i][0], acc[i][1]);
     }
     __syncthreads();
-    if (tid < NT) {
-        float *w = out + a.w_off[g] + k * cin * COUT + 2 * q;
+    for (int e = tid; e < 27 * CI * COUT; e += BWDW_TPB) {
+        const int kk = e / (CI * COUT), ci = (e / COUT) % CI, co = e % COUT;
+        float t = 0.f;
 #pragma unroll
-        for (int i = 0; i < CI; ++i) {
-            float lo = 0.f, hi = 0.f;
-#pragma unroll
-            for (int sidx = 0; sidx < TS; ++sidx) {
-                lo += s_part[((sidx * NT + kq) * CI + i) * 2];
-                hi += s_part[((sidx * NT + kq) * CI + i) * 2 + 1];
-            }
-            if (i < cin) w[i * COUT] = lo, w[i * COUT + 1] = hi;
-        }
-    } else if (tid >= 216 && tid - 216 < COUT && a.b_off[g] >= 0) {
-        out[a.b_off[g] + (tid - 216)] = bsum;
+        for (int sidx = 0; sidx < TS; ++sidx) t += s_part[sidx * 27 * CI * COUT + e];
+        if (ci < cin) out[a.w_off[g] + kk * cin * COUT + ci * COUT + co] = t;
     }
+    if (tid >= 216 && tid - 216 < COUT && a.b_off[g] >= 0) out[a.b_off[g] + (tid - 216)] = bsum;
 }
 
 // ------------------------------------------------------------------------------------------------
