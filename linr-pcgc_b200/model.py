@@ -159,6 +159,9 @@ class LINR_PCGC_Model(nn.Module):
     # ---- reference API ----------------------------------------------------------------------------------------
     def forward(self, inargs: Dict) -> torch.Tensor:
         t = self._tables_for(inargs, need_occ=True)
+        if not (torch.is_grad_enabled() and self.flat.requires_grad):
+            out = self._infer_runner(t.n_rows).forward(self.flat.detach(), t, want_bits=True)
+            return out["bits"].to(torch.float32).reshape(()).clone()
         return _ScaleBits.apply(self.flat, self, t)
 
     @torch.no_grad()
