@@ -64,7 +64,9 @@ def test_model_forward_backward_like_main_loop(env):
     ref = g["grad_flat"]
     assert np.abs(grad - ref).max() / np.abs(ref).max() < RTOL
     opt.step()                            # torch's own Adam on the flat parameter == the reference's per-tensor Adam
-    np.testing.assert_allclose(model.flat.detach().cpu().numpy(), g["flat_after_adam"], rtol=1e-5, atol=1e-6)
+    # the first Adam step moves every weight by lr * g / (|g| + 1e-8): elements whose gradient is ~1e-8 amplify the
+    # 1e-7-relative gradient difference, hence the absolute tolerance of 0.2 % of the step size lr = 0.01
+    np.testing.assert_allclose(model.flat.detach().cpu().numpy(), g["flat_after_adam"], rtol=1e-5, atol=2e-5)
 
 
 def test_model_encode_decode_codec_signatures(env):
