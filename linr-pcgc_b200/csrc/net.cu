@@ -99,6 +99,7 @@ struct Layout {
     int mlp_w1[8], mlp_b1[8], mlp_w2[8], mlp_b2[8];
     int pr_w[8], pr_b[8];
     BlockL ob[7];
+    BlockL blk8[8];  // {ob[0..6], bin}: the five inner layers of all eight blocks run as one 8-group launch
     int conv_first = 0;  // first parameter that is not SCE (embedding + scale MLPs)
     int total = 0;
     std::vector<int64_t> offsets;  // one per tensor, parameters() order
@@ -140,6 +141,8 @@ Layout make_layout(int S) {
     }
     for (int k = 0; k < 8; ++k) L.pr_w[k] = take(27 * 8 * 8), L.pr_b[k] = take(8);
     for (int k = 0; k < 7; ++k) L.ob[k] = block(k + 1);
+    for (int k = 0; k < 7; ++k) L.blk8[k] = L.ob[k];
+    L.blk8[7] = L.bin;
     L.total = o;
     return L;
 }
@@ -185,18 +188,20 @@ NetWs carve_net(void *ws, size_t bytes, int64_t R, int train, int P, int S) {
     WsCursor c(ws, bytes);
     const size_t r = (size_t)(R > 0 ? R : 1);
     w.f0 = c.take<float>(r * 8);
-    w.bi_y = c.take<float>(r * 8), w.bi_t1 = c.take<float>(r * 4), w.bi_t0 = c.take<float>(r * 4);
-    w.bi_t2 = c.take<float>(r * 4), w.bi_z = c.take<float>(r * 8);
     w.hh = c.take<float>(r * 64);
-    w.ob_y = c.take<float>(r * 56), w.ob_t1 = c.take<float>(r * 28), w.ob_t0 = c.take<float>(r * 28);
-    w.ob_t2 = c.take<float>(r * 28), w.ob_z = c.take<float>(r * 56);
+    // block activations: groups 0..6 = LDFE blocks, group 7 = GDFE block (block_in)
+    w.ob_y = c.take<float>(r * 64), w.ob_t1 = c.take<float>(r * 32), w.ob_t0 = c.take<float>(r * 32);
+    w.ob_t2 = c.take<float>(r * 32), w.ob_z = c.take<float>(r * 64);
+    w.bi_y = w.ob_y + 7 * R * 8, w.bi_t1 = w.ob_t1 + 7 * R * 4, w.bi_t0 = w.ob_t0 + 7 * R * 4;
+    w.bi_t2 = w.ob_t2 + 7 * R * 4, w.bi_z = w.ob_z + 7 * R * 8;
     w.hc = c.take<float>(r * 64);
     w.dzs = c.take<float>(r * 8);
     w.bits_partial = c.take<float>((size_t)ceil_div64(r, (ConvCfg<8, 8, 2>::ROWS)) * 8);
     if (train) {
-        w.dc = c.take<float>(r * 64), w.dhh = c.take<float>(r * 64), w.dg = c.take<float>(r * 8);
-        w.g_dz = c.take<float>(r * 56), w.g_dt0 = c.take<float>(r * 28), w.g_dy = c.take<float>(r * 56);
-        w.g_dt2 = c.take<float>(r * 28), w.g_dt1 = c.take<float>(r * 28);
+        w.dc = c.take<float>(r * 64), w.dhh = c.take<float>(r * 72);
+        w.dg = w.dhh + 8 * R * 8;  // group 8 of dhh: gradient of the GDFE output, next to the LDFE output gradients
+        w.g_dz = c.take<float>(r * 64), w.g_dt0 = c.take<float>(r * 32), w.g_dy = c.take<float>(r * 64);
+        w.g_dt2 = c.take<float>(r * 32), w.g_dt1 = c.take<float>(r * 32);
         w.df0 = c.take<float>(r * 8);
         w.partial = c.take<float>((size_t)w.n_chunks * P);
         w.sce_rec = c.take<float>((size_t)w.n_chunks * S * SCE_REC);
@@ -250,23 +255,26 @@ struct BlockBufs {  // activations of G blocks, group stride = R * C
     float *y, *t1, *t0, *t2, *z;
 };
 
-// Block(x) = ConvB(IRN(ReLU(ConvA(x))))  (models/upsample.py:88-97, models/resnet.py:55-60)
+// Block(x) = ConvB(IRN(ReLU(ConvA(x))))  (models/upsample.py:88-97, models/resnet.py:55-60), in three pieces so that
+// the five inner layers of the GDFE block and of the seven LDFE blocks can share one 8-group launch.
 // in_bits: input are the low (cin_base + g*cin_step) occupancy bits; else float x [R,8].
-void block_forward(const float *params, const BlockL *L, int G, const RowMap &m, bool in_bits, const uint8_t *occ, int cin_base,
-                   int cin_step, Tens x, const BlockBufs &b, Tens out, Tens res_out, cudaStream_t s) {
+void block_A_forward(const float *params, const BlockL *L, int G, const RowMap &m, bool in_bits, const uint8_t *occ, int cin_base,
+                     int cin_step, Tens x, float *y, cudaStream_t s) {
     const int64_t R = m.n_rows;
-    {  // ConvA + ReLU -> y
-        ConvArgs a = conv_args(m, params);
-        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].A_w, a.b_off[g] = L[g].A_b;
-        a.y = T(b.y, R * 8, 8), a.relu = 1;
-        if (in_bits) {
-            a.occ = occ, a.cin_base = cin_base, a.cin_step = cin_step;
-            launch_conv<8, 8, 1>(a, G, s);
-        } else {
-            a.x = x;
-            launch_conv<8, 8, 0>(a, G, s);
-        }
+    ConvArgs a = conv_args(m, params);  // ConvA + ReLU -> y
+    for (int g = 0; g < G; ++g) a.w_off[g] = L[g].A_w, a.b_off[g] = L[g].A_b;
+    a.y = T(y, R * 8, 8), a.relu = 1;
+    if (in_bits) {
+        a.occ = occ, a.cin_base = cin_base, a.cin_step = cin_step;
+        launch_conv<8, 8, 1>(a, G, s);
+    } else {
+        a.x = x;
+        launch_conv<8, 8, 0>(a, G, s);
     }
+}
+
+void block_mid_forward(const float *params, const BlockL *L, int G, const RowMap &m, const BlockBufs &b, cudaStream_t s) {
+    const int64_t R = m.n_rows;
     {  // conv1_0 (k=1) + ReLU -> t1
         PwArgs a = pw_args(R, params);
         for (int g = 0; g < G; ++g) a.w_off[g] = L[g].c10_w, a.b_off[g] = L[g].c10_b;
@@ -297,12 +305,22 @@ void block_forward(const float *params, const BlockL *L, int G, const RowMap &m,
         a.x = T(b.t2, R * 4, 4), a.y = T(b.z, R * 8, 8, 4), a.res = T(b.y, R * 8, 8, 4);
         launch_pw<4, 4>(a, G, s);
     }
-    {  // ConvB (+ residual g for the LDFE blocks: h_k = g + block, models/upsample.py:213)
-        ConvArgs a = conv_args(m, params);
-        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].B_w, a.b_off[g] = L[g].B_b;
-        a.x = T(b.z, R * 8, 8), a.y = out, a.res = res_out;
-        launch_conv<8, 8, 0>(a, G, s);
-    }
+}
+
+// ConvB (+ residual g for the LDFE blocks: h_k = g + block, models/upsample.py:213)
+void block_B_forward(const float *params, const BlockL *L, int G, const RowMap &m, float *z, Tens out, Tens res_out, cudaStream_t s) {
+    const int64_t R = m.n_rows;
+    ConvArgs a = conv_args(m, params);
+    for (int g = 0; g < G; ++g) a.w_off[g] = L[g].B_w, a.b_off[g] = L[g].B_b;
+    a.x = T(z, R * 8, 8), a.y = out, a.res = res_out;
+    launch_conv<8, 8, 0>(a, G, s);
+}
+
+void block_forward(const float *params, const BlockL *L, int G, const RowMap &m, bool in_bits, const uint8_t *occ, int cin_base,
+                   int cin_step, Tens x, const BlockBufs &b, Tens out, Tens res_out, cudaStream_t s) {
+    block_A_forward(params, L, G, m, in_bits, occ, cin_base, cin_step, x, b.y, s);
+    block_mid_forward(params, L, G, m, b, s);
+    block_B_forward(params, L, G, m, b.z, out, res_out, s);
 }
 
 struct BlockGrads {  // scratch of G blocks
@@ -341,11 +359,10 @@ void launch_pw_bwd_w(int64_t R, const NetWs &w, int P, const int *w_off, const i
     pw_bwd_w_kernel<CIN, COUT><<<grid, PWW_TPB, 0, s>>>(a);
 }
 
-// Backward of block_forward for G blocks.  dout: gradient wrt the block output.  If dx.p != null (block_in)
-// the gradient wrt the float input is produced too.
-void block_backward(const float *params, const BlockL *L, int G, const RowMap &m, const NetWs &w, int P, bool in_bits,
-                    const uint8_t *occ, int cin_base, int cin_step, Tens x, const BlockBufs &b, const BlockGrads &gr, Tens dout,
-                    Tens dx, cudaStream_t s) {
+// Backward of ConvB and of the five inner layers for G blocks.  dout: gradient wrt the block output; leaves the
+// gradient wrt ConvA's (post-ReLU) output in gr.dy for block_A_backward.
+void block_Bmid_backward(const float *params, const BlockL *L, int G, const RowMap &m, const NetWs &w, int P, const BlockBufs &b,
+                         const BlockGrads &gr, Tens dout, cudaStream_t s) {
     const int64_t R = m.n_rows;
     int wo[MAXG], bo[MAXG];
     auto offs = [&](int BlockL::*pw, int BlockL::*pb) {
@@ -406,8 +423,13 @@ void block_backward(const float *params, const BlockL *L, int G, const RowMap &m
         a.transpose = 1, a.x = dt1, a.y = dy, a.accum = 1, a.rmask = y;
         launch_pw<4, 8>(a, G, s);
     }
-    // ConvA
-    offs(&BlockL::A_w, &BlockL::A_b);
+}
+
+// Backward of ConvA for G blocks: weight gradient from (x | occupancy bits, dy); input gradient only if dx.p != null.
+void block_A_backward(const float *params, const BlockL *L, int G, const RowMap &m, const NetWs &w, int P, bool in_bits,
+                      const uint8_t *occ, int cin_base, int cin_step, Tens x, Tens dy, Tens dx, cudaStream_t s) {
+    int wo[MAXG], bo[MAXG];
+    for (int g = 0; g < G; ++g) wo[g] = L[g].A_w, bo[g] = L[g].A_b;
     if (in_bits) launch_bwd_w<8, 8, 1>(m, w, P, wo, bo, G, TN(), dy, occ, cin_base, cin_step, s);
     else launch_bwd_w<8, 8, 0>(m, w, P, wo, bo, G, x, dy, nullptr, 0, 0, s);
     if (dx.p) {
@@ -528,12 +550,15 @@ int linr_net_forward(const float *d_params, int scale_num, const linr_rows *rows
         ProfScope prof(K_SCE, R, s);
         sce_fwd_kernel<<<(unsigned)ceil_div64(R, SCE_TPB), SCE_TPB, 0, s>>>(a);
     }
-    // GDFE: g = block_in(f0) -> hh[0]
-    BlockBufs bi{w.bi_y, w.bi_t1, w.bi_t0, w.bi_t2, w.bi_z};
-    block_forward(d_params, &L.bin, 1, m, false, nullptr, 0, 0, T(w.f0, 0, 8), bi, T(w.hh, 0, 8), TN(), s);
-    // LDFE_k for k = 0..6, batched (teacher forcing): hh[k+1] = g + block_k(occ[:, :k+1])
-    BlockBufs ob{w.ob_y, w.ob_t1, w.ob_t0, w.ob_t2, w.ob_z};
-    block_forward(d_params, L.ob, 7, m, true, rows->d_occ, 1, 1, TN(), ob, T(w.hh + R * 8, R * 8, 8), T(w.hh, 0, 8), s);
+    // ConvA of the GDFE block (float input f0, group 7) and of the 7 LDFE blocks (occupancy bits, teacher forcing)
+    BlockBufs all{w.ob_y, w.ob_t1, w.ob_t0, w.ob_t2, w.ob_z};
+    block_A_forward(d_params, &L.bin, 1, m, false, nullptr, 0, 0, T(w.f0, 0, 8), w.bi_y, s);
+    block_A_forward(d_params, L.ob, 7, m, true, rows->d_occ, 1, 1, TN(), w.ob_y, s);
+    // the five inner layers of all eight blocks in 8-group launches
+    block_mid_forward(d_params, L.blk8, 8, m, all, s);
+    // ConvB: g = block_in(f0) -> hh[0], then hh[k+1] = g + LDFE_k(occ[:, :k+1])
+    block_B_forward(d_params, &L.bin, 1, m, w.bi_z, T(w.hh, 0, 8), TN(), s);
+    block_B_forward(d_params, L.ob, 7, m, w.ob_z, T(w.hh + R * 8, R * 8, 8), T(w.hh, 0, 8), s);
     // 8 heads
     const bool want_bits = d_bits != nullptr || train;
     head_forward(d_params, L, m, 0, 8, T(w.hh, R * 8, 8), train ? w.hc : nullptr, rows->d_occ, d_probs, d_cdf,
@@ -591,13 +616,13 @@ int linr_net_backward(const float *d_params, int scale_num, const linr_rows *row
         ProfScope prof(K_REDUCE, R, s);
         sum_groups_kernel<<<(unsigned)ceil_div64(R * 2, 256), 256, 0, s>>>(w.dhh, R * 8, 8, R * 2, w.dg);
     }
-    // LDFE blocks (inputs are occupancy bits: no input gradient)
-    BlockBufs ob{w.ob_y, w.ob_t1, w.ob_t0, w.ob_t2, w.ob_z};
+    // ConvB + inner layers of all eight blocks (output gradients: dhh[1..7] for the LDFE blocks, dg = dhh[8] for GDFE)
+    BlockBufs all{w.ob_y, w.ob_t1, w.ob_t0, w.ob_t2, w.ob_z};
     BlockGrads gr{w.g_dz, w.g_dt0, w.g_dy, w.g_dt2, w.g_dt1};
-    block_backward(d_params, L.ob, 7, m, w, P, true, rows->d_occ, 1, 1, TN(), ob, gr, T(w.dhh + R * 8, R * 8, 8), TN(), s);
-    // GDFE block
-    BlockBufs bi{w.bi_y, w.bi_t1, w.bi_t0, w.bi_t2, w.bi_z};
-    block_backward(d_params, &L.bin, 1, m, w, P, false, nullptr, 0, 0, T(w.f0, 0, 8), bi, gr, T(w.dg, 0, 8), T(w.df0, 0, 8), s);
+    block_Bmid_backward(d_params, L.blk8, 8, m, w, P, all, gr, T(w.dhh + R * 8, R * 8, 8), s);
+    // ConvA: LDFE blocks read occupancy bits (no input gradient); the GDFE block (group 7) propagates to f0
+    block_A_backward(d_params, L.ob, 7, m, w, P, true, rows->d_occ, 1, 1, TN(), T(w.g_dy, R * 8, 8), TN(), s);
+    block_A_backward(d_params, &L.bin, 1, m, w, P, false, nullptr, 0, 0, T(w.f0, 0, 8), T(w.g_dy + 7 * R * 8, 0, 8), T(w.df0, 0, 8), s);
     // SCE
     SceArgs sa = sce_args(d_params, L, rows);
     sa.df0 = T(w.df0, 0, 8), sa.chunk = w.chunk;

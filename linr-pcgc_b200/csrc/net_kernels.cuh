@@ -89,7 +89,7 @@ constexpr int CONV_TPB = 128;
 // wavefront pipe, not the FMA pipe, is what saturates first)
 template <int CIN, int COUT, int MODE>
 struct ConvCfg {
-    static constexpr int RPT = (CIN == 8 && COUT == 8 && MODE != 1) ? 4 : 2;
+    static constexpr int RPT = (CIN == COUT && MODE != 1) ? 4 : 2;
     static constexpr int ROWS = CONV_TPB * RPT;  // rows per block
 };
 
@@ -341,7 +341,7 @@ struct BwdWCfg {
 // wavefronts than the multiply itself.  Thread = (row split, offset k, output-channel quad): it walks its rows in
 // ascending order, four gathers in flight, with dW[k][0..CI-1][4q..4q+3] in registers (packed FFMA2).
 template <int CIN, int COUT, int MODE>
-__global__ void __launch_bounds__(BWDW_TPB) conv27_bwd_w_kernel(const BwdWArgs a) {
+__global__ void __launch_bounds__(BWDW_TPB, (MODE == 1) ? 2 : ((CIN == 4 && COUT == 4) ? 5 : 4)) conv27_bwd_w_kernel(const BwdWArgs a) {
     using Cfg = BwdWCfg<CIN, COUT, MODE>;
     constexpr int CI = Cfg::CI, QT = Cfg::QT, NT = Cfg::NT, TS = Cfg::TS, TPS = Cfg::TPS;
     static_assert(NT * TS == 216 && TPS * TS == BW_T && TPS % 4 == 0, "thread mapping");
