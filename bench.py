@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--dp", action="store_true", help="intra-GOP data parallel instead of one GOP per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-sample-rows", type=int, default=60000)
+    ap.add_argument("--cpu-sample-rows", type=int, default=75000)
     return ap.parse_args()
 
 

@@ -121,7 +121,7 @@ typedef struct {
     const int32_t *d_anchor; /* [9,ld]   */
     const uint32_t *d_mask;  /* [n_rows] */
     const uint8_t *d_nbr7;   /* [n_rows] */
-    const uint8_t *d_scale;  /* [n_rows] scale index of each row */
+    const uint8_t *d_scale;  /* [n_rows] scale index of each row, non-decreasing (scales are concatenated in order) */
     const uint8_t *d_occ;    /* [n_rows] 8-bit child occupancy (teacher forcing / decoded so far) */
 } linr_rows;
 

@@ -341,10 +341,11 @@ struct BwdWCfg {
 // wavefronts than the multiply itself.  Thread = (row split, offset k, output-channel quad): it walks its rows in
 // ascending order, four gathers in flight, with dW[k][0..CI-1][4q..4q+3] in registers (packed FFMA2).
 template <int CIN, int COUT, int MODE>
-__global__ void __launch_bounds__(BWDW_TPB, (MODE == 1) ? 2 : ((CIN == 4 && COUT == 4) ? 5 : 4)) conv27_bwd_w_kernel(const BwdWArgs a) {
+__global__ void __launch_bounds__(BWDW_TPB, (MODE == 1) ? 4 : ((CIN == 4 && COUT == 4) ? 5 : 4)) conv27_bwd_w_kernel(const BwdWArgs a) {
     using Cfg = BwdWCfg<CIN, COUT, MODE>;
     constexpr int CI = Cfg::CI, QT = Cfg::QT, NT = Cfg::NT, TS = Cfg::TS, TPS = Cfg::TPS;
-    static_assert(NT * TS == 216 && TPS * TS == BW_T && TPS % 4 == 0, "thread mapping");
+    constexpr int PF = (MODE == 1) ? 2 : 4;  // gathers in flight per thread
+    static_assert(NT * TS == 216 && TPS * TS == BW_T && TPS % PF == 0, "thread mapping");
     extern __shared__ __align__(16) float s_buf[];
     uint32_t *s_mask = reinterpret_cast<uint32_t *>(s_buf);
     int *s_anch = reinterpret_cast<int *>(s_buf) + BW_T;
@@ -382,10 +383,10 @@ __global__ void __launch_bounds__(BWDW_TPB, (MODE == 1) ? 2 : ((CIN == 4 && COUT
         if (is_mm) {
             const int tb = ts * TPS;
 #pragma unroll 1
-            for (int tt = 0; tt < TPS; tt += 4) {
-                float xv[4][CI];
+            for (int tt = 0; tt < TPS; tt += PF) {
+                float xv[PF][CI];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < PF; ++u) {
                     const int t = tb + tt + u;
                     const uint32_t m3 = (s_mask[t] >> (3 * c)) & 7u;
 #pragma unroll
@@ -402,7 +403,7 @@ __global__ void __launch_bounds__(BWDW_TPB, (MODE == 1) ? 2 : ((CIN == 4 && COUT
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < PF; ++u) {
                     const ulonglong2 d = *reinterpret_cast<const ulonglong2 *>(s_dy + (tb + tt + u) * COUT + 4 * qd);
 #pragma unroll
                     for (int i = 0; i < CI; ++i) {
@@ -603,13 +604,15 @@ __device__ __forceinline__ void sce_stage_scale(const SceArgs &a, int s, float *
 
 __global__ void __launch_bounds__(SCE_TPB) sce_fwd_kernel(const SceArgs a) {
     __shared__ float s_p[MAXS * SCE_SM];
-    if (a.scale_fixed >= 0) sce_stage_scale(a, a.scale_fixed, s_p);
-    else
-        for (int s = 0; s < a.scale_num; ++s) sce_stage_scale(a, s, s_p + s * SCE_SM);
+    // rows are grouped by scale in ascending order (frame.py), so a block only needs the scales of its own row range
+    const int64_t row0 = blockIdx.x * (int64_t)SCE_TPB, rowl = min(row0 + SCE_TPB, a.n_rows) - 1;
+    const int s_lo = a.scale_fixed >= 0 ? a.scale_fixed : a.scale[row0];
+    const int s_hi = a.scale_fixed >= 0 ? a.scale_fixed : a.scale[rowl];
+    for (int s = s_lo; s <= s_hi; ++s) sce_stage_scale(a, s, s_p + (s - s_lo) * SCE_SM);
     __syncthreads();
-    const int64_t row = blockIdx.x * (int64_t)SCE_TPB + threadIdx.x;
+    const int64_t row = row0 + threadIdx.x;
     if (row >= a.n_rows) return;
-    const float *p = a.scale_fixed >= 0 ? s_p : s_p + a.scale[row] * SCE_SM;
+    const float *p = a.scale_fixed >= 0 ? s_p : s_p + (a.scale[row] - s_lo) * SCE_SM;
     const unsigned bits = a.nbr7[row];
     float out[8];
 #pragma unroll
@@ -633,12 +636,22 @@ __global__ void __launch_bounds__(SCE_TPB) sce_fwd_kernel(const SceArgs a) {
 constexpr int SCE_REC = 128 + 8 + 112 + 16;
 __global__ void __launch_bounds__(256) sce_bwd_kernel(const SceArgs a, float *rec /* [n_chunks][scale_num][SCE_REC] */) {
     __shared__ float s_p[MAXS * SCE_SM];
-    for (int s = 0; s < a.scale_num; ++s) sce_stage_scale(a, s, s_p + s * SCE_SM);
-    __syncthreads();
     const int j = threadIdx.x >> 4, sub = threadIdx.x & 15;
     const int64_t r0 = blockIdx.x * a.chunk, r1 = min(r0 + a.chunk, a.n_rows);
     float *out = rec + (int64_t)blockIdx.x * a.scale_num * SCE_REC;
+    // scales present in this chunk (rows are grouped by scale, ascending); the other records are zero
+    int s_lo = a.scale_num, s_hi = -1;
+    if (r0 < r1) {
+        s_lo = a.scale_fixed >= 0 ? a.scale_fixed : a.scale[r0];
+        s_hi = a.scale_fixed >= 0 ? a.scale_fixed : a.scale[r1 - 1];
+    }
+    for (int s = s_lo; s <= s_hi; ++s) sce_stage_scale(a, s, s_p + s * SCE_SM);
+    __syncthreads();
     for (int s = 0; s < a.scale_num; ++s) {
+        if (s < s_lo || s > s_hi) {
+            for (int i = threadIdx.x; i < SCE_REC; i += blockDim.x) out[s * SCE_REC + i] = 0.f;
+            continue;
+        }
         const float *p = s_p + s * SCE_SM;
         float aw2[8], aw1[7], ab1 = 0.f, ab2 = 0.f;
 #pragma unroll
