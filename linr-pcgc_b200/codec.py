@@ -7,6 +7,7 @@ coder (csrc/rc_host.cpp) runs on the host over the independent streams in parall
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -78,39 +79,140 @@ def encode_frame(runner: NetRunner, params: torch.Tensor, frame: Frame, threads:
     return [pack_bitstream(streams[8 * s: 8 * s + 8]) for s in range(frame.n_scales)]
 
 
-def decode_scale(runner: NetRunner, params: torch.Tensor, coords: torch.Tensor, scale_idx: int, data: bytes):
-    """One scale: parents `coords` (sorted unique, CUDA int32 [N,3]) + its bitstream -> uint8 occupancy [N] (CUDA)."""
+def encode_frames(runner: NetRunner, params: torch.Tensor, frames: Sequence[Frame], threads: Optional[int] = None,
+                  depth: int = 4, coders: int = 2) -> List[List[bytes]]:
+    """Encode several frames with the GPU and the host coder overlapped: while the range coder works on frame i
+    (C code, GIL released), the network forward and the CDF download of frame i+1 are already running.  `depth` pinned
+    staging sets bound the frames in flight, `coders` frames are range-coded at the same time (the 8 stage streams of
+    the finest scale hold 3/4 of a frame's symbols, so one frame cannot use more than ~8 cores).  Same bytes as
+    `encode_frame` frame by frame."""
+    from concurrent.futures import ThreadPoolExecutor
+    if not frames:
+        return []
+    cap = max(f.tables.n_rows for f in frames)
+    sets = [(torch.empty((8, max(cap, 1)), dtype=torch.int16).pin_memory(), torch.empty(max(cap, 1), dtype=torch.uint8).pin_memory())
+            for _ in range(min(depth, len(frames)))]
+    events = [torch.cuda.Event() for _ in sets]
+    pending = [None] * len(sets)
+    out: List[Optional[List[bytes]]] = [None] * len(frames)
+
+    def code(i: int, slot: int):
+        f = frames[i]
+        events[slot].synchronize()
+        cdf, occ = sets[slot][0].numpy().view(np.uint16), sets[slot][1].numpy()
+        cdfs, syms, shifts = [], [], []
+        for s in range(f.n_scales):
+            a, b = f.scale_off[s], f.scale_off[s + 1]
+            for k in range(8):
+                cdfs.append(cdf[k, a:b])
+                syms.append(occ[a:b])
+                shifts.append(k)
+        streams = rc.encode_binary_batch(cdfs, syms, shifts, threads or max(4, (os.cpu_count() or 8) // max(1, coders)))
+        return [pack_bitstream(streams[8 * s: 8 * s + 8]) for s in range(f.n_scales)]
+
+    with ThreadPoolExecutor(max_workers=max(1, coders)) as pool:
+        for i, f in enumerate(frames):
+            slot = i % len(sets)
+            if pending[slot] is not None:           # the staging set is free once its frame has been coded
+                j, fut = pending[slot]
+                out[j] = fut.result()
+            R = f.tables.n_rows
+            res = runner.forward(params, f.tables, train=False, want_cdf=True, want_bits=False)
+            sets[slot][0][:, :R].copy_(res["cdf"], non_blocking=True)
+            sets[slot][1][:R].copy_(f.tables.occ, non_blocking=True)
+            events[slot].record()
+            pending[slot] = (i, pool.submit(code, i, slot))
+        for p in pending:
+            if p is not None:
+                out[p[0]] = p[1].result()
+    return out  # type: ignore[return-value]
+
+
+class _DecodeCtx:
+    """Per-thread decode state: runner + pinned staging buffers, reused across scales and frames."""
+
+    def __init__(self, scale_num: int, device, runner: Optional[NetRunner] = None):
+        self.runner = runner if runner is not None else NetRunner(scale_num, 1, device, train=False)
+        self.cap = 0
+        self.h_cdf = self.h_sym = None
+
+    def reserve(self, n: int):
+        if n > self.cap:
+            self.cap = max(n, 2 * self.cap, 1024)
+            self.h_cdf = torch.empty(self.cap, dtype=torch.int16).pin_memory()
+            self.h_sym = torch.empty(self.cap, dtype=torch.uint8).pin_memory()
+
+
+def decode_scale(runner: NetRunner, params: torch.Tensor, coords: torch.Tensor, scale_idx: int, data: bytes,
+                 ctx: Optional[_DecodeCtx] = None):
+    """One scale: parents `coords` (sorted unique, CUDA int32 [N,3]) + its bitstream -> uint8 occupancy [N] (CUDA).
+    The 8 stages are strictly sequential (CNP.decode, models/upsample.py:249-295): stage k's network input contains
+    the bits decoded in stages < k."""
     n = int(coords.shape[0])
     dev = coords.device
+    if ctx is None:
+        ctx = _DecodeCtx(runner.S, dev, runner)
+    ctx.reserve(n)
     scale = torch.full((n,), scale_idx, dtype=torch.uint8, device=dev)
     occ = torch.zeros(n, dtype=torch.uint8, device=dev)
     t = build_tables(coords, scale, occ)
     streams = unpack_bitstream(data)
     runner.decode_begin(params, t)
-    h_cdf = torch.empty(n, dtype=torch.int16).pin_memory()
-    h_sym = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_cdf, h_sym = ctx.h_cdf[:n], ctx.h_sym[:n]
     d_sym = torch.empty(n, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
     for k in range(8):
         d_cdf, _ = runner.decode_stage(params, t, k)
         h_cdf.copy_(d_cdf, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        sym = rc.decode_binary(h_cdf.numpy().view(np.uint16), streams[k], n)
-        h_sym.numpy()[:] = sym
+        stream.synchronize()
+        rc.decode_binary_into(h_cdf.numpy().view(np.uint16), streams[k], h_sym.numpy())
         d_sym.copy_(h_sym, non_blocking=True)
         runner.occ_set_stage(occ, d_sym, k)
     return occ, t
 
 
 def decode_frame(runner: NetRunner, params: torch.Tensor, all_bytes: Sequence[bytes], low_coords: torch.Tensor,
-                 low_bits: int = 8) -> torch.Tensor:
+                 low_bits: int = 8, ctx: Optional[_DecodeCtx] = None) -> torch.Tensor:
     """decode_one_frame (decoder.py:153-176): coarse-to-fine; returns the full-resolution sorted coords (CUDA int32)."""
     cur = low_coords
     bits = max(low_bits, 1)
     for s in range(len(all_bytes) - 1, -1, -1):
-        occ, _ = decode_scale(runner, params, cur, s, all_bytes[s])
+        occ, _ = decode_scale(runner, params, cur, s, all_bytes[s], ctx)
         bits += 1
         cur = octree_up(cur, occ, bits)
     return cur
+
+
+def decode_frames(params: torch.Tensor, scale_num: int, jobs: Sequence, workers: int = 8) -> List[torch.Tensor]:
+    """Decode independent frames concurrently (frames of a GOP only share the model): one host thread, CUDA stream
+    and runner per in-flight frame, so the 56 device<->host round trips of a frame overlap with those of the others
+    and the serial range decoders run on different cores.  jobs: (all_bytes, low_coords CUDA int32 [N,3])."""
+    from concurrent.futures import ThreadPoolExecutor
+    import threading
+    if not jobs:
+        return []
+    dev = params.device
+    workers = max(1, min(workers, len(jobs)))
+    local = threading.local()
+    main_stream = torch.cuda.current_stream(dev)
+    ready = torch.cuda.Event()
+    ready.record(main_stream)
+
+    def run(job):
+        if not hasattr(local, "ctx"):
+            torch.cuda.set_device(dev)
+            local.stream = torch.cuda.Stream(dev)
+            local.ctx = _DecodeCtx(scale_num, dev)
+        with torch.cuda.stream(local.stream):
+            local.stream.wait_event(ready)
+            out = decode_frame(local.ctx.runner, params, job[0], job[1], ctx=local.ctx)
+            local.stream.synchronize()
+        return out
+
+    if workers == 1:
+        return [run(j) for j in jobs]
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        return list(pool.map(run, jobs))
 
 
 def pack_low_xyz(low_coords: Sequence[np.ndarray], mins: Sequence[np.ndarray]) -> bytes:

@@ -65,7 +65,7 @@ def encode_gop(frames: Sequence[Frame], flat_params: torch.Tensor, scale_num: in
     recon = comp["recon_ret"]
     if runner is None:
         runner = NetRunner(scale_num, max(f.tables.n_rows for f in frames), flat_params.device, train=False)
-    frame_bytes = [codec.encode_frame(runner, recon, f, threads) for f in frames]
+    frame_bytes = codec.encode_frames(runner, recon, frames, threads)
     lows = [f.scale_coords(f.n_scales - 1).cpu().numpy() for f in frames]
     low = codec.pack_low_xyz(lows, [f.coord_min for f in frames])
     side = dict(mu=comp["mu"], b=comp["b"], min_param=comp["min_param"], max_param=comp["max_param"],
@@ -73,7 +73,7 @@ def encode_gop(frames: Sequence[Frame], flat_params: torch.Tensor, scale_num: in
     return EncodedGop(scale_num, side, comp["final_bytes"], comp["bit_real"], low, frame_bytes, [f.point_num for f in frames])
 
 
-def decode_gop(enc: EncodedGop, device="cuda", runner: Optional[NetRunner] = None) -> List[torch.Tensor]:
+def decode_gop(enc: EncodedGop, device="cuda", workers: Optional[int] = None) -> List[torch.Tensor]:
     """decode_one_gop (decoder.py:51-147): model from its bitstream, frames coarse-to-fine; returns the original
     (min-restored) sorted coordinates of every frame as CUDA int32 [Np,3]."""
     n = P.offsets(P.param_spec(enc.scale_num))[-1]
@@ -81,14 +81,9 @@ def decode_gop(enc: EncodedGop, device="cuda", runner: Optional[NetRunner] = Non
     d["final_bytes"] = enc.model_bytes
     flat = model_compression.decompress_model(d, n, device)
     lows, mins = codec.unpack_low_xyz(enc.low_enc_bytes)
-    if runner is None:
-        runner = NetRunner(enc.scale_num, 1, device, train=False)
-    out = []
-    for i, fb in enumerate(enc.frame_bytes):
-        low = torch.from_numpy(lows[i]).to(device)
-        xyz = codec.decode_frame(runner, flat, fb, low)
-        out.append(xyz + torch.from_numpy(mins[i].copy()).to(device))
-    return out
+    jobs = [(fb, torch.from_numpy(lows[i]).to(device)) for i, fb in enumerate(enc.frame_bytes)]
+    dec = codec.decode_frames(flat, enc.scale_num, jobs, workers=workers or min(16, os.cpu_count() or 8))
+    return [xyz + torch.from_numpy(mins[i].copy()).to(device) for i, xyz in enumerate(dec)]
 
 
 def overfit_encode_gop(points: Sequence[torch.Tensor], epochs: int, state: Optional[OptimState] = None,

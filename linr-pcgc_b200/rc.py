@@ -42,6 +42,16 @@ def decode_binary(cdf_mid: np.ndarray, data: bytes, n: int) -> np.ndarray:
     return out
 
 
+def decode_binary_into(cdf_mid: np.ndarray, data: bytes, out: np.ndarray) -> None:
+    """decode_binary writing into a caller-owned uint8 buffer (pinned staging memory in the decoder)."""
+    lib = _lib.load()
+    cdf_mid = np.ascontiguousarray(cdf_mid).view(np.uint16)
+    buf = np.frombuffer(data, dtype=np.uint8)
+    assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"]
+    _lib.check(lib.linr_rc_decode_binary(_p(cdf_mid), _p(buf) if len(buf) else None, len(buf), _p(out), int(out.shape[0])),
+               "linr_rc_decode_binary")
+
+
 def encode_binary_batch(cdf_mids: Sequence[np.ndarray], syms: Sequence[np.ndarray], shifts: Sequence[int] | None = None,
                         threads: int | None = None) -> List[bytes]:
     """Independent streams (8 stages x S scales of a frame) on a pool of host threads.

@@ -346,3 +346,21 @@ def test_full_size_encode_decode_lossless(L, O):
     all_bytes = L.codec.encode_frame(run, flat, fr)
     dec = L.codec.decode_frame(run, flat, all_bytes, fr.scale_coords(S - 1).contiguous())
     assert dec.shape == fr.xyz.shape and (dec == fr.xyz).all()
+
+
+def test_concurrent_decode_mvub_sized(L, O):
+    """MVUB-shaped frames (~300k points, BASELINE.json configs[4]): pipelined encode of several frames, then the
+    frames decoded concurrently on separate streams/threads; bytes identical to the frame-by-frame encoder."""
+    pts = L.synth.make_sequence("mvub10", 3, device="cuda")
+    frames = [L.frame.prepare_frame(p, None, 64) for p in pts]
+    S = frames[0].n_scales
+    flat = O.flatten_params(O.init_params(S, seed=4), S).cuda()
+    run = L.net.NetRunner(S, max(f.tables.n_rows for f in frames), "cuda", train=False)
+    enc = L.codec.encode_frames(run, flat, frames, threads=4)
+    for f, e in zip(frames, enc):
+        assert e == L.codec.encode_frame(run, flat, f, threads=2)
+    jobs = [(e, f.scale_coords(f.n_scales - 1).contiguous()) for f, e in zip(frames, enc)]
+    for workers in (1, 3):
+        dec = L.codec.decode_frames(flat, S, jobs, workers=workers)
+        for d, f in zip(dec, frames):
+            assert d.shape == f.xyz.shape and (d == f.xyz).all()
