@@ -43,11 +43,13 @@ class _Pinned:
         self.occ = None
 
     def get(self, rows: int):
-        if self.cdf is None or self.cdf.shape[1] < rows:
+        """Contiguous pinned views [8, rows] int16 and [rows] uint8 (a strided D2H copy would bounce through a
+        temporary and synchronise)."""
+        if self.cdf is None or self.cdf.numel() < 8 * rows:
             cap = max(rows, 1)
-            self.cdf = torch.empty((8, cap), dtype=torch.int16).pin_memory()
+            self.cdf = torch.empty(8 * cap, dtype=torch.int16).pin_memory()
             self.occ = torch.empty(cap, dtype=torch.uint8).pin_memory()
-        return self.cdf, self.occ
+        return self.cdf[: 8 * rows].view(8, rows), self.occ[:rows]
 
 
 _pinned = _Pinned()
@@ -59,8 +61,8 @@ def frame_cdfs_to_host(runner: NetRunner, params: torch.Tensor, frame: Frame):
     R = t.n_rows
     out = runner.forward(params, t, train=False, want_cdf=True, want_bits=False)
     h_cdf, h_occ = _pinned.get(R)
-    h_cdf[:, :R].copy_(out["cdf"], non_blocking=True)
-    h_occ[:R].copy_(t.occ, non_blocking=True)
+    h_cdf.copy_(out["cdf"], non_blocking=True)
+    h_occ.copy_(t.occ, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     return h_cdf.numpy().view(np.uint16), h_occ.numpy(), R
 
@@ -90,7 +92,7 @@ def encode_frames(runner: NetRunner, params: torch.Tensor, frames: Sequence[Fram
     if not frames:
         return []
     cap = max(f.tables.n_rows for f in frames)
-    sets = [(torch.empty((8, max(cap, 1)), dtype=torch.int16).pin_memory(), torch.empty(max(cap, 1), dtype=torch.uint8).pin_memory())
+    sets = [(torch.empty(8 * max(cap, 1), dtype=torch.int16).pin_memory(), torch.empty(max(cap, 1), dtype=torch.uint8).pin_memory())
             for _ in range(min(depth, len(frames)))]
     events = [torch.cuda.Event() for _ in sets]
     pending = [None] * len(sets)
@@ -99,7 +101,8 @@ def encode_frames(runner: NetRunner, params: torch.Tensor, frames: Sequence[Fram
     def code(i: int, slot: int):
         f = frames[i]
         events[slot].synchronize()
-        cdf, occ = sets[slot][0].numpy().view(np.uint16), sets[slot][1].numpy()
+        R = f.tables.n_rows
+        cdf, occ = sets[slot][0][: 8 * R].view(8, R).numpy().view(np.uint16), sets[slot][1][:R].numpy()
         cdfs, syms, shifts = [], [], []
         for s in range(f.n_scales):
             a, b = f.scale_off[s], f.scale_off[s + 1]
@@ -118,7 +121,7 @@ def encode_frames(runner: NetRunner, params: torch.Tensor, frames: Sequence[Fram
                 out[j] = fut.result()
             R = f.tables.n_rows
             res = runner.forward(params, f.tables, train=False, want_cdf=True, want_bits=False)
-            sets[slot][0][:, :R].copy_(res["cdf"], non_blocking=True)
+            sets[slot][0][: 8 * R].view(8, R).copy_(res["cdf"], non_blocking=True)   # contiguous: one async memcpy
             sets[slot][1][:R].copy_(f.tables.occ, non_blocking=True)
             events[slot].record()
             pending[slot] = (i, pool.submit(code, i, slot))
@@ -183,6 +186,9 @@ def decode_frame(runner: NetRunner, params: torch.Tensor, all_bytes: Sequence[by
     return cur
 
 
+_ctx_pool: dict = {}   # (device, scale_num) -> idle decode contexts (workspaces are large: keep them across calls)
+
+
 def decode_frames(params: torch.Tensor, scale_num: int, jobs: Sequence, workers: int = 8) -> List[torch.Tensor]:
     """Decode independent frames concurrently (frames of a GOP only share the model): one host thread, CUDA stream
     and runner per in-flight frame, so the 56 device<->host round trips of a frame overlap with those of the others
@@ -194,6 +200,10 @@ def decode_frames(params: torch.Tensor, scale_num: int, jobs: Sequence, workers:
     dev = params.device
     workers = max(1, min(workers, len(jobs)))
     local = threading.local()
+    key = (str(dev), scale_num)
+    idle = _ctx_pool.setdefault(key, [])
+    lock = threading.Lock()
+    used = []
     main_stream = torch.cuda.current_stream(dev)
     ready = torch.cuda.Event()
     ready.record(main_stream)
@@ -201,18 +211,27 @@ def decode_frames(params: torch.Tensor, scale_num: int, jobs: Sequence, workers:
     def run(job):
         if not hasattr(local, "ctx"):
             torch.cuda.set_device(dev)
-            local.stream = torch.cuda.Stream(dev)
-            local.ctx = _DecodeCtx(scale_num, dev)
+            with lock:
+                local.ctx = idle.pop() if idle else None
+            if local.ctx is None:
+                local.ctx = _DecodeCtx(scale_num, dev)
+                local.ctx.stream = torch.cuda.Stream(dev)
+            local.stream = local.ctx.stream
+            with lock:
+                used.append(local.ctx)
         with torch.cuda.stream(local.stream):
             local.stream.wait_event(ready)
             out = decode_frame(local.ctx.runner, params, job[0], job[1], ctx=local.ctx)
             local.stream.synchronize()
         return out
 
-    if workers == 1:
-        return [run(j) for j in jobs]
-    with ThreadPoolExecutor(max_workers=workers) as pool:
-        return list(pool.map(run, jobs))
+    try:
+        if workers == 1:
+            return [run(j) for j in jobs]
+        with ThreadPoolExecutor(max_workers=workers) as pool:
+            return list(pool.map(run, jobs))
+    finally:
+        idle.extend(used)
 
 
 def pack_low_xyz(low_coords: Sequence[np.ndarray], mins: Sequence[np.ndarray]) -> bytes:

@@ -174,7 +174,7 @@ struct NetWs {
 
 int chunks_for(int64_t R) {
     int64_t nb = ceil_div64(R, 64);
-    int64_t cap = 4 * (int64_t)linr_sm_count();  // weight-gradient partial sums: one per row chunk
+    int64_t cap = 2 * (int64_t)linr_sm_count();  // weight-gradient partial sums: one per row chunk
     if (nb > cap) nb = cap;
     if (nb < 1) nb = 1;
     return (int)nb;
