@@ -336,16 +336,11 @@ void launch_bwd_w(const RowMap &m, const NetWs &w, int P, const int *w_off, cons
     for (int g = 0; g < G; ++g) a.w_off[g] = w_off[g], a.b_off[g] = b_off[g];
     a.x = x, a.dy = dy, a.occ = occ, a.cin_base = cin_base, a.cin_step = cin_step;
     a.partial = w.partial, a.P = P, a.chunk = w.chunk;
-    dim3 grid((unsigned)w.n_chunks, (unsigned)G);
+    using Cfg = BwdWCfg<CIN, COUT, MODE>;
+    dim3 grid((unsigned)Cfg::GX, (unsigned)w.n_chunks, (unsigned)G);  // offset slots fastest: blocks sharing a row chunk run together
     constexpr int cls = MODE == 1 ? K_BWDWBITS : (COUT == 8 ? K_BWDW88 : (CIN == 8 ? K_BWDW84 : K_BWDW44));
     ProfScope prof(cls, m.n_rows * G, s);
-    using Cfg = BwdWCfg<CIN, COUT, MODE>;
-    static bool attr_set = false;  // > 48 KB of dynamic shared memory needs the opt-in once per kernel
-    if (!attr_set) {
-        cudaFuncSetAttribute(conv27_bwd_w_kernel<CIN, COUT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-        attr_set = true;
-    }
-    conv27_bwd_w_kernel<CIN, COUT, MODE><<<grid, BWDW_TPB, Cfg::SMEM, s>>>(a);
+    conv27_bwd_w_kernel<CIN, COUT, MODE><<<grid, Cfg::TPB, 0, s>>>(a);
 }
 template <int CIN, int COUT>
 void launch_pw_bwd_w(int64_t R, const NetWs &w, int P, const int *w_off, const int *b_off, int G, Tens x, Tens dy, cudaStream_t s) {

@@ -86,10 +86,11 @@ struct ConvArgs {
 
 constexpr int CONV_TPB = 128;
 // rows per thread: the weights of an offset are read from shared memory once for all of them (the L1/shared
-// wavefront pipe, not the FMA pipe, is what saturates first)
+// wavefront pipe, not the FMA pipe, is what saturates first).  Measured (round 1): 4 rows help every 8-channel-input
+// conv; the 4-channel-input and bit-input convs are gather-bound and lose occupancy with more rows.
 template <int CIN, int COUT, int MODE>
 struct ConvCfg {
-    static constexpr int RPT = (CIN == COUT && MODE != 1) ? 4 : 2;
+    static constexpr int RPT = (CIN == 8 && MODE != 1) ? 4 : 2;
     static constexpr int ROWS = CONV_TPB * RPT;  // rows per block
 };
 
@@ -304,11 +305,14 @@ __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
 
 // ------------------------------------------------------------------------------------------------
 // Weight gradient of the 3x3x3 conv: dW[k][ci][co] = sum_o x[nbr(o,k)][ci] * dy[o][co], db = sum_o dy[o].
-// Tile-staged: a block walks its row chunk in tiles of BW_T rows.  Stage: the gathered inputs of all 27 offsets
-// (zero rows for absent neighbours) and the dy tile go to shared memory with many independent loads in flight.
-// Compute: thread (split, k, q) keeps dW[k][0..CI-1][2q..2q+1] in registers (packed FFMA2) and walks its share of
-// the tile rows in ascending order.  Partial sums: per thread over its rows, then over the BW row splits, then over
-// the chunks (finalize kernel) -- every order fixed, no floating-point atomics.
+// Mapping: ONE WARP PER KERNEL OFFSET (slot), LANE = ROW.  A warp walks its row chunk 32 consecutive rows at a time:
+// the kernel-map words, the dy rows and the gathered neighbour rows of 32 consecutive output rows are (nearly)
+// consecutive in memory, so every load is coalesced and an L1 wavefront serves ~4 rows (the previous mapping, a warp
+// across 16 offsets of ONE row, touched ~one 128-byte line per useful pair and was bound by the L1 wavefront pipe).
+// Every lane keeps a private dW[k] (CI x COUT, packed FFMA2) over its rows; no shared memory, no barriers; loads of
+// step s+1 are issued before the FMAs of step s.  At the end the 32 lane-private copies are summed by a transposing
+// butterfly (fixed order), one partial vector per (row chunk, offset) -- summed over chunks by finalize_grad_kernel.
+// Slot 27/NK (an extra warp) sums dy for the bias gradient.  No floating-point atomics anywhere.
 // ------------------------------------------------------------------------------------------------
 struct BwdWArgs {
     RowMap map;
@@ -318,124 +322,179 @@ struct BwdWArgs {
     int cin_base, cin_step;
     float *partial;  // [n_chunks][P]
     int64_t P;
-    int64_t chunk;  // rows per chunk (multiple of BW_T)
+    int64_t chunk;  // rows per chunk (multiple of 32)
 };
-constexpr int BWDW_TPB = 224;
-constexpr int BW_T = 128;  // rows per tile
+constexpr int BW_T = 128;  // chunk granularity (rows)
 
 template <int CIN, int COUT, int MODE>
 struct BwdWCfg {
-    static constexpr int CI = (MODE == 1) ? 8 : CIN;   // accumulated input width (bit inputs: up to 7 of 8 used)
-    static constexpr int QT = COUT / 4;                // threads per offset, each owning 4 output channels (2 packed pairs)
-    static constexpr int NT = 27 * QT;                 // threads per row split
-    static constexpr int TS = 216 / NT;                // row splits per tile (4 for COUT 8, 8 for COUT 4)
-    static constexpr int TPS = BW_T / TS;              // tile rows per split
-    static constexpr int STAGE = BW_T + BW_T * 9 + BW_T * COUT;  // words: mask, anchors [t][9], dy tile [t][COUT]
-    static constexpr int PART = 216 * CI * 4;          // floats needed to combine the row splits at the end
-    static constexpr int WORDS = STAGE > PART ? STAGE : PART;
-    static constexpr size_t SMEM = (size_t)WORDS * 4;
+    static constexpr int CI = (MODE == 1) ? 7 : CIN;                    // accumulated input width (bit inputs: up to 7)
+    static constexpr int NK = (CIN == 4 && COUT == 4) ? 3 : 1;           // offsets per thread: the dz planes of its column
+    static constexpr int SLOTS = 27 / NK + 1;                            // warps of work per (chunk, group); last = bias
+    static constexpr int WPB = (NK == 3) ? 5 : 7;                        // warps per block
+    static constexpr int GX = (SLOTS + WPB - 1) / WPB;                   // blocks per (chunk, group)
+    static constexpr int TPB = 32 * WPB;
+    // register cap: 128 -> 4 warps per SM sub-partition (16 K registers each), 80 -> 6
+    static constexpr int MAXREG = (CIN == 8 && COUT == 4) ? 80 : 128;
+    static constexpr int XW = (MODE == 1) ? 1 : CIN;                     // registers of one gathered neighbour
+    static constexpr int DEPTH = (CIN == 8 && COUT == 4) ? 2 : 3;        // software pipeline depth (row steps)
+    static constexpr int V = NK * CI * COUT;                             // accumulators per thread
+    static constexpr int VP = V <= 32 ? 32 : 64;                         // padded for the butterfly
+    static_assert(V <= 64, "accumulator tile");
 };
 
-// Only the kernel-map slice and the dy tile are staged in shared memory (coalesced); the gathered input rows are
-// read straight from global memory / L1 with one 256-bit load per (row, offset) -- staging them costs more L1
-// wavefronts than the multiply itself.  Thread = (row split, offset k, output-channel quad): it walks its rows in
-// ascending order, four gathers in flight, with dW[k][0..CI-1][4q..4q+3] in registers (packed FFMA2).
-template <int CIN, int COUT, int MODE>
-__global__ void __launch_bounds__(BWDW_TPB, (MODE == 1) ? 4 : ((CIN == 4 && COUT == 4) ? 5 : 4)) conv27_bwd_w_kernel(const BwdWArgs a) {
-    using Cfg = BwdWCfg<CIN, COUT, MODE>;
-    constexpr int CI = Cfg::CI, QT = Cfg::QT, NT = Cfg::NT, TS = Cfg::TS, TPS = Cfg::TPS;
-    constexpr int PF = (MODE == 1) ? 2 : 4;  // gathers in flight per thread
-    static_assert(NT * TS == 216 && TPS * TS == BW_T && TPS % PF == 0, "thread mapping");
-    extern __shared__ __align__(16) float s_buf[];
-    uint32_t *s_mask = reinterpret_cast<uint32_t *>(s_buf);
-    int *s_anch = reinterpret_cast<int *>(s_buf) + BW_T;
-    float *s_dy = s_buf + BW_T + BW_T * 9;
-    const int g = blockIdx.y;
-    const int cin = (MODE == 1) ? (a.cin_base + g * a.cin_step) : CIN;
-    const int tid = threadIdx.x;
-    const int64_t r0 = blockIdx.x * a.chunk;
-    const int64_t r1 = min(r0 + a.chunk, a.map.n_rows);
-    float *out = a.partial + blockIdx.x * a.P;
-
-    const bool is_mm = tid < 216;
-    const int ts = tid / NT, kq = tid % NT, k = kq / QT, qd = kq % QT;
-    const int c = k % 9, j = k / 9;
-    const uint32_t jbit = 1u << j, jlow = jbit - 1u;
-    u64 acc[CI][2];  // dW[k][ci][4qd .. 4qd+3] over this thread's rows
-#pragma unroll
-    for (int i = 0; i < CI; ++i) acc[i][0] = acc[i][1] = 0ull;
-    float bsum = 0.f;
-
-    for (int64_t t0 = r0; t0 < r1; t0 += BW_T) {
-        // ---- stage the map slice and the dy tile (rows past the chunk end: empty mask, zero dy)
-        for (int i = tid; i < BW_T; i += BWDW_TPB) s_mask[i] = (t0 + i < r1) ? a.map.mask[t0 + i] : 0u;
-        for (int i = tid; i < BW_T * 9; i += BWDW_TPB) {
-            const int cc = i / BW_T, t = i % BW_T;
-            s_anch[t * 9 + cc] = (t0 + t < r1) ? a.map.anchor[cc * a.map.ld + t0 + t] : 0;
-        }
-        for (int i = tid; i < BW_T * COUT / 4; i += BWDW_TPB) {
-            const int t = i / (COUT / 4), part = i % (COUT / 4);
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (t0 + t < r1) v = *reinterpret_cast<const float4 *>(tptr(a.dy, g, t0 + t) + 4 * part);
-            *reinterpret_cast<float4 *>(s_dy + t * COUT + 4 * part) = v;
-        }
-        __syncthreads();
-        if (is_mm) {
-            const int tb = ts * TPS;
-#pragma unroll 1
-            for (int tt = 0; tt < TPS; tt += PF) {
-                float xv[PF][CI];
-#pragma unroll
-                for (int u = 0; u < PF; ++u) {
-                    const int t = tb + tt + u;
-                    const uint32_t m3 = (s_mask[t] >> (3 * c)) & 7u;
-#pragma unroll
-                    for (int i = 0; i < CI; ++i) xv[u][i] = 0.f;
-                    if (m3 & jbit) {
-                        const int nb = s_anch[t * 9 + c] + __popc(m3 & jlow);
-                        if (MODE == 1) {
-                            const unsigned o = a.occ[nb];
-#pragma unroll
-                            for (int i = 0; i < 7; ++i) xv[u][i] = ((o >> i) & 1u) ? 1.f : 0.f;  // channels >= cin are never written out
-                        } else {
-                            gather_row<CIN>(tptr(a.x, g, nb), xv[u]);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < PF; ++u) {
-                    const ulonglong2 d = *reinterpret_cast<const ulonglong2 *>(s_dy + (tb + tt + u) * COUT + 4 * qd);
-#pragma unroll
-                    for (int i = 0; i < CI; ++i) {
-                        const u64 xx = pack2(xv[u][i], xv[u][i]);
-                        ffma2_acc(acc[i][0], xx, d.x);
-                        ffma2_acc(acc[i][1], xx, d.y);
-                    }
-                }
-            }
-        } else if (tid - 216 < COUT) {
-            const float *ds = s_dy + (tid - 216);
-#pragma unroll 8
-            for (int t = 0; t < BW_T; ++t) bsum += ds[t * COUT];
-        }
-        __syncthreads();
+template <int C>
+__device__ __forceinline__ void load_row_nc2(const float *p, u64 (&v)[C / 2]) {
+    if constexpr (C == 8) {
+        asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
+    } else {
+        asm("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(v[0]), "=l"(v[1]) : "l"(p));
     }
-    // ---- combine the row splits in order, write this chunk's partial: s_part[ts][k][ci][co]
-    float *s_part = s_buf;
-    if (is_mm) {
+}
+
+template <int CIN, int COUT, int MODE>
+__global__ void __launch_bounds__(BwdWCfg<CIN, COUT, MODE>::TPB) __maxnreg__((BwdWCfg<CIN, COUT, MODE>::MAXREG)) conv27_bwd_w_kernel(const BwdWArgs a) {
+    using Cfg = BwdWCfg<CIN, COUT, MODE>;
+    constexpr int CI = Cfg::CI, NK = Cfg::NK, XW = Cfg::XW, HQ = COUT / 2, V = Cfg::V, VP = Cfg::VP;
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * Cfg::WPB + (threadIdx.x >> 5);
+    if (slot >= Cfg::SLOTS) return;
+    const int g = blockIdx.z;
+    const int cin = (MODE == 1) ? (a.cin_base + g * a.cin_step) : CIN;
+    const int64_t r0 = blockIdx.y * a.chunk;
+    const int64_t r1 = min(r0 + a.chunk, a.map.n_rows);
+    float *out = a.partial + blockIdx.y * a.P;
+    const float *dyg = a.dy.p + g * a.dy.gs + a.dy.off;
+    const int dld = a.dy.ld;
+
+    if (slot == Cfg::SLOTS - 1) {  // ---- bias gradient: column sums of dy over the chunk
+        if (a.b_off[g] < 0) return;
+        u64 bs[HQ];
+#pragma unroll
+        for (int q = 0; q < HQ; ++q) bs[q] = 0ull;
+        for (int64_t r = r0 + lane; r < r1; r += 32) {
+            u64 d[HQ];
+            load_row_nc2<COUT>(dyg + r * dld, d);
+#pragma unroll
+            for (int q = 0; q < HQ; ++q) fadd2_acc(bs[q], d[q]);
+        }
+        float v[COUT];
+#pragma unroll
+        for (int q = 0; q < HQ; ++q) unpack2(bs[q], v[2 * q], v[2 * q + 1]);
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) v[co] += __shfl_xor_sync(0xffffffffu, v[co], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) out[a.b_off[g] + co] = v[co];
+        }
+        return;
+    }
+
+    // ---- weight gradient of offsets k = c + 9*(j0 + nk), nk < NK
+    const int c = (NK == 3) ? slot : slot % 9, j0 = (NK == 3) ? 0 : slot / 9;
+    const int32_t *anch = a.map.anchor + c * a.map.ld;
+    const float *xg = (MODE == 1) ? nullptr : (a.x.p + g * a.x.gs + a.x.off);
+    const int xld = a.x.ld;
+    u64 acc[NK][CI][HQ];
+#pragma unroll
+    for (int n = 0; n < NK; ++n)
 #pragma unroll
         for (int i = 0; i < CI; ++i)
-            *reinterpret_cast<ulonglong2 *>(s_part + ((ts * 27 + k) * CI + i) * COUT + 4 * qd) = make_ulonglong2(acc[i][0], acc[i][1]);
-    }
-    __syncthreads();
-    for (int e = tid; e < 27 * CI * COUT; e += BWDW_TPB) {
-        const int kk = e / (CI * COUT), ci = (e / COUT) % CI, co = e % COUT;
-        float t = 0.f;
 #pragma unroll
-        for (int sidx = 0; sidx < TS; ++sidx) t += s_part[sidx * 27 * CI * COUT + e];
-        if (ci < cin) out[a.w_off[g] + kk * cin * COUT + ci * COUT + co] = t;
+            for (int q = 0; q < HQ; ++q) acc[n][i][q] = 0ull;
+
+    // stage A (kernel-map words) runs two steps ahead, stage B (neighbour rows, dy) one step ahead of the FMAs
+    auto loadA = [&](int64_t r, uint32_t &m3, int &an) {
+        m3 = 0u, an = 0;
+        if (r < r1) {
+            m3 = (a.map.mask[r] >> (3 * c)) & 7u;
+            an = anch[r];
+        }
+    };
+    auto loadB = [&](int64_t r, uint32_t m3, int an, float (&xb)[NK][XW], u64 (&db)[HQ]) {
+#pragma unroll
+        for (int q = 0; q < HQ; ++q) db[q] = 0ull;
+        if (r < r1) load_row_nc2<COUT>(dyg + r * dld, db);
+#pragma unroll
+        for (int n = 0; n < NK; ++n) {
+            const int j = j0 + n;
+#pragma unroll
+            for (int i = 0; i < XW; ++i) xb[n][i] = 0.f;
+            if ((m3 >> j) & 1u) {
+                const int nb = an + __popc(m3 & ((1u << j) - 1u));
+                if constexpr (MODE == 1) xb[n][0] = __uint_as_float((unsigned)a.occ[nb]);
+                else gather_row<CIN>(xg + (int64_t)nb * xld, xb[n]);
+            }
+        }
+    };
+    auto fma = [&](const float (&xb)[NK][XW], const u64 (&db)[HQ]) {
+#pragma unroll
+        for (int n = 0; n < NK; ++n) {
+#pragma unroll
+            for (int i = 0; i < CI; ++i) {
+                float xs;
+                if (MODE == 1) xs = ((__float_as_uint(xb[n][0]) >> i) & 1u) ? 1.f : 0.f;
+                else xs = xb[n][i];
+                const u64 xx = pack2(xs, xs);
+#pragma unroll
+                for (int q = 0; q < HQ; ++q) ffma2_acc(acc[n][i][q], xx, db[q]);
+            }
+        }
+    };
+
+    constexpr int D = Cfg::DEPTH;  // ring of D (neighbour row, dy row) buffers: loads run D-1 steps ahead of the FMAs
+    float xb[D][NK][XW];
+    u64 db[D][HQ];
+    uint32_t mA;
+    int aA;
+    int64_t r = r0 + lane;
+#pragma unroll
+    for (int u = 0; u < D - 1; ++u) {
+        loadA(r + 32 * u, mA, aA);
+        loadB(r + 32 * u, mA, aA, xb[u], db[u]);
     }
-    if (tid >= 216 && tid - 216 < COUT && a.b_off[g] >= 0) out[a.b_off[g] + (tid - 216)] = bsum;
+    loadA(r + 32 * (D - 1), mA, aA);
+#pragma unroll 1
+    for (; r - lane < r1; r += 32 * D) {  // warp-uniform trip count; rows past the chunk end contribute exact zeros
+#pragma unroll
+        for (int u = 0; u < D; ++u) {
+            loadB(r + 32 * (u + D - 1), mA, aA, xb[(u + D - 1) % D], db[(u + D - 1) % D]);
+            loadA(r + 32 * (u + D), mA, aA);
+            fma(xb[u], db[u]);
+        }
+    }
+
+    // ---- sum the 32 lane-private copies: transposing butterfly, lane ends up with elements lane*VP/32 + i
+    float v[VP];
+#pragma unroll
+    for (int e = 0; e < VP; ++e) v[e] = 0.f;
+#pragma unroll
+    for (int n = 0; n < NK; ++n)
+#pragma unroll
+        for (int i = 0; i < CI; ++i)
+#pragma unroll
+            for (int q = 0; q < HQ; ++q) unpack2(acc[n][i][q], v[(n * CI + i) * COUT + 2 * q], v[(n * CI + i) * COUT + 2 * q + 1]);
+#pragma unroll
+    for (int o = 16, H = VP / 2; o; o >>= 1, H >>= 1) {
+        const bool up = lane & o;
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            const float keep = up ? v[i + H] : v[i], send = up ? v[i] : v[i + H];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < VP / 32; ++i) {
+        const int e = lane * (VP / 32) + i;
+        if (e < V) {
+            const int n = e / (CI * COUT), ci = (e / COUT) % CI, co = e % COUT;
+            const int k = c + 9 * (j0 + n);
+            if (ci < cin) out[a.w_off[g] + k * cin * COUT + ci * COUT + co] = v[i];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
