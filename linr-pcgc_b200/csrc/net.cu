@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 
+#include <mutex>
 #include <vector>
 
 #include "net_kernels.cuh"
@@ -40,6 +41,7 @@ struct ProfState {
     std::vector<cudaEvent_t> ev[K_NCLASS];  // begin/end pairs recorded so far
     std::vector<cudaEvent_t> pool;          // recycled events
     double ms_done[K_NCLASS] = {0};
+    std::mutex mu;  // launches come from several host threads (GOP coder, concurrent decoders)
 } g_prof;
 const char *const kNames[K_NCLASS] = {"conv27<8,8>", "conv27<8,4>", "conv27<4,8>", "conv27<4,4>", "conv27_bits<8>", "conv27_head",
                                       "bwd_w<8,8>", "bwd_w<8,4>", "bwd_w<4,4>", "bwd_w_bits<8>", "pointwise", "pointwise_bwd_w",
@@ -67,6 +69,7 @@ void prof_drain(int c) {
 }
 }  // namespace
 void prof_begin(int cls, int64_t units, cudaStream_t s) {
+    std::lock_guard<std::mutex> lock(g_prof.mu);
     g_prof.launches[cls] += 1;
     g_prof.units[cls] += units;
     if (g_prof.mask >> cls & 1u) {
@@ -76,6 +79,7 @@ void prof_begin(int cls, int64_t units, cudaStream_t s) {
     }
 }
 void prof_end(int cls, cudaStream_t s) {
+    std::lock_guard<std::mutex> lock(g_prof.mu);
     if (g_prof.mask >> cls & 1u) {
         cudaEvent_t e = prof_event();
         cudaEventRecord(e, s);
@@ -488,6 +492,7 @@ int linr_device_info(int device, int *sm_count, int64_t *l2_bytes) {
 }
 
 int linr_prof_enable(uint32_t class_mask) {
+    std::lock_guard<std::mutex> lock(g_prof.mu);
     for (int c = 0; c < K_NCLASS; ++c) {
         prof_drain(c);
         g_prof.launches[c] = 0, g_prof.units[c] = 0, g_prof.ms_done[c] = 0.0;
@@ -497,6 +502,7 @@ int linr_prof_enable(uint32_t class_mask) {
 }
 int linr_prof_read(int cls, double *ms_total, int64_t *launches, int64_t *units) {
     LINR_REQUIRE(cls >= 0 && cls < K_NCLASS, "profiler class out of range");
+    std::lock_guard<std::mutex> lock(g_prof.mu);
     prof_drain(cls);
     if (ms_total) *ms_total = g_prof.ms_done[cls];
     if (launches) *launches = g_prof.launches[cls];

@@ -86,15 +86,71 @@ def decode_gop(enc: EncodedGop, device="cuda", workers: Optional[int] = None) ->
     return [xyz + torch.from_numpy(mins[i].copy()).to(device) for i, xyz in enumerate(dec)]
 
 
+class GopCoder:
+    """Codes GOP g in the background while the caller overfits GOP g+1.
+
+    The coding of a GOP needs only its frames (read-only tables) and a snapshot of the trained parameters, and every
+    GOP after the first starts from GOP 0's state (main.py:102-104), so consecutive GOPs pipeline: the network
+    forward of the coder runs on a side stream, the CDF download and the range coder on host threads, the next GOP's
+    overfitting on the caller's stream.  One GOP is in flight at a time (staging buffers and the inference workspace
+    are reused); `submit` of the next GOP first collects the previous one."""
+
+    def __init__(self, device="cuda", bitdepth: int = 8, threads: Optional[int] = None):
+        from concurrent.futures import ThreadPoolExecutor
+        self.device = torch.device(device)
+        self.bitdepth, self.threads = bitdepth, threads
+        self.side = torch.cuda.Stream(self.device)
+        self.pool = ThreadPoolExecutor(max_workers=1)
+        self.pending = None
+        self.runner: Optional[NetRunner] = None
+        self.results: List[EncodedGop] = []
+
+    def submit(self, frames: Sequence[Frame], flat_params: torch.Tensor, scale_num: int):
+        """Call on the stream that trained `flat_params`; returns a future of the EncodedGop."""
+        self.collect()
+        snap = flat_params.clone()            # the caller keeps training this vector
+        snap.record_stream(self.side)
+        ready = torch.cuda.Event()
+        ready.record()
+        if self.runner is None or self.runner.S != scale_num:
+            self.runner = NetRunner(scale_num, max(f.tables.n_rows for f in frames), self.device, train=False)
+        runner = self.runner
+
+        def work():
+            torch.cuda.set_device(self.device)
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(ready)
+                enc = encode_gop(frames, snap, scale_num, self.bitdepth, runner=runner, threads=self.threads)
+                self.side.synchronize()
+            return enc
+
+        self.pending = self.pool.submit(work)
+        return self.pending
+
+    def collect(self) -> Optional[EncodedGop]:
+        """Wait for the GOP in flight (if any) and order the caller's stream after the coder's."""
+        if self.pending is None:
+            return None
+        enc = self.pending.result()
+        self.pending = None
+        torch.cuda.current_stream(self.device).wait_stream(self.side)
+        self.results.append(enc)
+        return enc
+
+
 def overfit_encode_gop(points: Sequence[torch.Tensor], epochs: int, state: Optional[OptimState] = None,
                        scale_num: Optional[int] = None, min_point_num: int = 64, bitdepth: int = 8, device="cuda",
-                       seed: Optional[int] = None, trainer_kwargs: Optional[Dict] = None, threads: Optional[int] = None):
+                       seed: Optional[int] = None, trainer_kwargs: Optional[Dict] = None, threads: Optional[int] = None,
+                       coder: Optional[GopCoder] = None):
     """The whole per-GOP hot path from raw points (host or device) to bitstreams.
-    Returns (EncodedGop, OptimState to seed the next GOP, per-epoch losses)."""
+    Returns (EncodedGop, OptimState to seed the next GOP, per-epoch losses); with a `GopCoder` the first element is a
+    future and the coding overlaps whatever the caller does next (normally the next GOP)."""
     frames = prepare_gop(points, scale_num, min_point_num, device)
     S = scale_num or frames[0].n_scales
     tr = GopTrainer(S, device, seed=seed, state=state, max_rows=max(f.tables.n_rows for f in frames), **(trainer_kwargs or {}))
     losses = tr.fit(frames, epochs)
+    if coder is not None:
+        return coder.submit(frames, tr.state.params, S), tr.state, losses
     enc = encode_gop(frames, tr.state.params, S, bitdepth, threads=threads)
     return enc, tr.state, losses
 

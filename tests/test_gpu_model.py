@@ -112,6 +112,32 @@ def test_gop_pipeline_overfit_encode_decode(env):
     assert l2[0] < losses[0] and st2.step == 21
 
 
+def test_background_gop_coder_matches_serial_encode(env):
+    """GopCoder (coding of GOP g on a side stream + host threads while the caller keeps training) returns the same
+    bytes as the serial encode of the same parameter snapshot, even though training continues on the live vector."""
+    import torch
+    from linr_pcgc_b200 import pipeline, synth
+    from linr_pcgc_b200.trainer import GopTrainer
+    pts = synth.make_sequence("tiny", 3)
+    frames = pipeline.prepare_gop([p.cuda() for p in pts])
+    S = frames[0].n_scales
+    tr = GopTrainer(S, "cuda", seed=5, max_rows=max(f.tables.n_rows for f in frames))
+    tr.fit(frames, 2)
+    snap = tr.state.params.clone()
+    coder = pipeline.GopCoder("cuda")
+    fut = coder.submit(frames, tr.state.params, S)
+    tr.fit(frames, 2)                              # keeps changing tr.state.params while the coder runs
+    enc_bg = coder.collect()
+    assert fut.done() and coder.collect() is None
+    enc_serial = pipeline.encode_gop(frames, snap, S)
+    assert enc_bg.frame_bytes == enc_serial.frame_bytes and enc_bg.model_bytes == enc_serial.model_bytes
+    assert enc_bg.low_enc_bytes == enc_serial.low_enc_bytes and enc_bg.side_info == enc_serial.side_info
+    fut2, st, _ = pipeline.overfit_encode_gop([p.cuda() for p in pts], epochs=1, seed=5, coder=coder)
+    dec = pipeline.decode_gop(coder.collect())
+    for d, p in zip(dec, pts):
+        assert bool((d.cpu() == p).all())
+
+
 def test_cli_end_to_end_lossless(env, tmp_path):
     from linr_pcgc_b200 import main as cli, pointio, synth
     ori = tmp_path / "ori"
