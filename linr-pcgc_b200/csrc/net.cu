@@ -178,7 +178,7 @@ struct NetWs {
 
 int chunks_for(int64_t R) {
     int64_t nb = ceil_div64(R, 64);
-    int64_t cap = 2 * (int64_t)linr_sm_count();  // weight-gradient partial sums: one per row chunk
+    int64_t cap = (int64_t)linr_sm_count();  // weight-gradient partial sums: one per row chunk
     if (nb > cap) nb = cap;
     if (nb < 1) nb = 1;
     return (int)nb;
@@ -600,10 +600,10 @@ int linr_net_backward(const float *d_params, int scale_num, const linr_rows *row
         a.partial = w.partial, a.P = P, a.chunk = w.chunk;
         {
             ProfScope prof(K_HEADBWD, R * 8, s);
-            head_bwd_rows_kernel<<<dim3((unsigned)ceil_div64(R, 256), 8), 256, 0, s>>>(a);
+            head_bwd_rows_kernel<<<dim3((unsigned)ceil_div64(R, 128 * HEAD_RPT), 8), 128, 0, s>>>(a);
         }
         ProfScope prof(K_HEADBWD, R * 8, s);
-        head_bwd_w_kernel<<<dim3((unsigned)w.n_chunks, 8), 192, 0, s>>>(a);
+        head_bwd_w_kernel<<<dim3((unsigned)w.n_chunks, 8), 256, 0, s>>>(a);
     }
     launch_bwd_w<8, 8, 0>(m, w, P, L.pr_w, L.pr_b, 8, T(w.hh, R * 8, 8), T(w.dc, R * 8, 8), nullptr, 0, 0, s);
     {
@@ -629,11 +629,11 @@ int linr_net_backward(const float *d_params, int scale_num, const linr_rows *row
     sa.df0 = T(w.df0, 0, 8), sa.chunk = w.chunk;
     {
         ProfScope prof(K_SCE, R, s);
-        sce_bwd_kernel<<<(unsigned)w.n_chunks, 256, 0, s>>>(sa, w.sce_rec);
+        sce_bwd_kernel<<<(unsigned)w.n_chunks, SCE_BWD_TPB, 0, s>>>(sa, w.sce_rec);
     }
     {
         ProfScope prof(K_SCE, L.S, s);
-        sce_finalize_kernel<<<(unsigned)L.S, 256, 0, s>>>(sa, w.sce_rec, w.n_chunks, d_grad);
+        sce_finalize_kernel<<<(unsigned)L.S, 1024, 0, s>>>(sa, w.sce_rec, w.n_chunks, d_grad);
     }
     const int64_t cnt = P - L.conv_first;
     {

@@ -303,6 +303,24 @@ __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
     }
 }
 
+
+// Sum N (= 32 or 64) lane-private values over the 32 lanes of a warp with a transposing butterfly: 31 (63) shuffles
+// instead of 5 per value.  Afterwards lane l holds the totals of elements l*N/32 .. l*N/32 + N/32 - 1 in v[0 .. N/32).
+// The pairing order is fixed, so the result is bitwise reproducible.
+template <int N>
+__device__ __forceinline__ void warp_transpose_reduce(float (&v)[N], int lane) {
+    static_assert(N == 32 || N == 64, "padded accumulator count");
+#pragma unroll
+    for (int o = 16, H = N / 2; o; o >>= 1, H >>= 1) {
+        const bool up = lane & o;
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            const float keep = up ? v[i + H] : v[i], send = up ? v[i] : v[i + H];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Weight gradient of the 3x3x3 conv: dW[k][ci][co] = sum_o x[nbr(o,k)][ci] * dy[o][co], db = sum_o dy[o].
 // Mapping: ONE WARP PER KERNEL OFFSET (slot), LANE = ROW.  A warp walks its row chunk 32 consecutive rows at a time:
@@ -477,15 +495,7 @@ __global__ void __launch_bounds__(BwdWCfg<CIN, COUT, MODE>::TPB) __maxnreg__((Bw
         for (int i = 0; i < CI; ++i)
 #pragma unroll
             for (int q = 0; q < HQ; ++q) unpack2(acc[n][i][q], v[(n * CI + i) * COUT + 2 * q], v[(n * CI + i) * COUT + 2 * q + 1]);
-#pragma unroll
-    for (int o = 16, H = VP / 2; o; o >>= 1, H >>= 1) {
-        const bool up = lane & o;
-#pragma unroll
-        for (int i = 0; i < H; ++i) {
-            const float keep = up ? v[i + H] : v[i], send = up ? v[i] : v[i + H];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-        }
-    }
+    warp_transpose_reduce<VP>(v, lane);
 #pragma unroll
     for (int i = 0; i < VP / 32; ++i) {
         const int e = lane * (VP / 32) + i;
@@ -689,16 +699,17 @@ __global__ void __launch_bounds__(SCE_TPB) sce_fwd_kernel(const SceArgs a) {
     store_row<8>(tptr(a.f0, 0, row), out);
 }
 
-// Backward: thread = (hidden unit j, row subset sub of 16); flushes per scale segment inside its chunk.
-// Per (chunk, scale) it writes: dW2[:, j] (8), dW1n[j][0..6], db1eff[j]; threads j<8 also db2[j].
+// Backward: warp w < 8 owns hidden units 2w, 2w+1, LANE = ROW (coalesced nbr7 / df0 loads, lane-private sums, one
+// transposing butterfly per (chunk, scale)); warp 8 sums df0 for the second-layer bias.  Rows are grouped by scale,
+// so a chunk touches few scales; the records of the others are zero-filled.
 // Layout of one SCE partial record per scale (floats): [dW2 8*16][db2 8][dW1n 16*7][db1eff 16] = 264
 constexpr int SCE_REC = 128 + 8 + 112 + 16;
-__global__ void __launch_bounds__(256) sce_bwd_kernel(const SceArgs a, float *rec /* [n_chunks][scale_num][SCE_REC] */) {
+constexpr int SCE_BWD_TPB = 288;
+__global__ void __launch_bounds__(SCE_BWD_TPB) sce_bwd_kernel(const SceArgs a, float *rec /* [n_chunks][scale_num][SCE_REC] */) {
     __shared__ float s_p[MAXS * SCE_SM];
-    const int j = threadIdx.x >> 4, sub = threadIdx.x & 15;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t r0 = blockIdx.x * a.chunk, r1 = min(r0 + a.chunk, a.n_rows);
     float *out = rec + (int64_t)blockIdx.x * a.scale_num * SCE_REC;
-    // scales present in this chunk (rows are grouped by scale, ascending); the other records are zero
     int s_lo = a.scale_num, s_hi = -1;
     if (r0 < r1) {
         s_lo = a.scale_fixed >= 0 ? a.scale_fixed : a.scale[r0];
@@ -712,54 +723,65 @@ __global__ void __launch_bounds__(256) sce_bwd_kernel(const SceArgs a, float *re
             continue;
         }
         const float *p = s_p + s * SCE_SM;
-        float aw2[8], aw1[7], ab1 = 0.f, ab2 = 0.f;
+        float v[32];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) aw2[c] = 0.f;
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        if (w < 8) {
+            // per hidden unit jj: v[16jj + c] = dW2[c][j], v[16jj + 8 + b] = dW1n[j][b], v[16jj + 15] = db1eff[j]
+            float b1e[2], w1n[2][7], w2c[2][8];
 #pragma unroll
-        for (int b = 0; b < 7; ++b) aw1[b] = 0.f;
-        for (int64_t r = r0 + sub; r < r1; r += 16) {
-            const int rs = a.scale_fixed >= 0 ? a.scale_fixed : a.scale[r];
-            if (rs != s) continue;
-            const unsigned bits = a.nbr7[r];
-            float d[8];
-            load_row<8>(tptr(a.df0, 0, r), d);
-            float h = p[j];
+            for (int jj = 0; jj < 2; ++jj) {
+                const int j = 2 * w + jj;
+                b1e[jj] = p[j];
 #pragma unroll
-            for (int b = 0; b < 7; ++b)
-                if ((bits >> b) & 1u) h += p[16 + j * 7 + b];
-            h = fmaxf(h, 0.f);
-            float dh = 0.f;
+                for (int b = 0; b < 7; ++b) w1n[jj][b] = p[16 + j * 7 + b];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                aw2[c] = fmaf(d[c], h, aw2[c]);
-                dh = fmaf(p[128 + c * 16 + j], d[c], dh);
+                for (int c = 0; c < 8; ++c) w2c[jj][c] = p[128 + c * 16 + j];
             }
-            dh = h > 0.f ? dh : 0.f;
+#pragma unroll 2
+            for (int64_t r = r0 + lane; r < r1; r += 32) {
+                const int rs = a.scale_fixed >= 0 ? a.scale_fixed : a.scale[r];
+                if (rs != s) continue;
+                const unsigned bits = a.nbr7[r];
+                float d[8];
+                load_row<8>(tptr(a.df0, 0, r), d);
 #pragma unroll
-            for (int b = 0; b < 7; ++b)
-                if ((bits >> b) & 1u) aw1[b] += dh;
-            ab1 += dh;
+                for (int jj = 0; jj < 2; ++jj) {
+                    float h = b1e[jj];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) ab2 += (c == j) ? d[c] : 0.f;
-        }
-        // reduce over the 16 subsets (16 adjacent lanes)
+                    for (int b = 0; b < 7; ++b)
+                        if ((bits >> b) & 1u) h += w1n[jj][b];   // same order as the forward kernel
+                    h = fmaxf(h, 0.f);
+                    float dh = 0.f;
 #pragma unroll
-        for (int o = 1; o < 16; o <<= 1) {
+                    for (int c = 0; c < 8; ++c) {
+                        v[16 * jj + c] = fmaf(d[c], h, v[16 * jj + c]);
+                        dh = fmaf(w2c[jj][c], d[c], dh);
+                    }
+                    dh = h > 0.f ? dh : 0.f;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) aw2[c] += __shfl_xor_sync(0xffffffffu, aw2[c], o);
-#pragma unroll
-            for (int b = 0; b < 7; ++b) aw1[b] += __shfl_xor_sync(0xffffffffu, aw1[b], o);
-            ab1 += __shfl_xor_sync(0xffffffffu, ab1, o);
-            ab2 += __shfl_xor_sync(0xffffffffu, ab2, o);
-        }
-        if (sub == 0) {
+                    for (int b = 0; b < 7; ++b)
+                        if ((bits >> b) & 1u) v[16 * jj + 8 + b] += dh;
+                    v[16 * jj + 15] += dh;
+                }
+            }
+            warp_transpose_reduce<32>(v, lane);
+            const int j = 2 * w + (lane >> 4), e = lane & 15;
             float *o = out + s * SCE_REC;
+            if (e < 8) o[e * 16 + j] = v[0];
+            else if (e < 15) o[136 + j * 7 + (e - 8)] = v[0];
+            else o[248 + j] = v[0];
+        } else {
+            for (int64_t r = r0 + lane; r < r1; r += 32) {
+                const int rs = a.scale_fixed >= 0 ? a.scale_fixed : a.scale[r];
+                if (rs != s) continue;
+                float d[8];
+                load_row<8>(tptr(a.df0, 0, r), d);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) o[c * 16 + j] = aw2[c];
-            if (j < 8) o[128 + j] = ab2;
-#pragma unroll
-            for (int b = 0; b < 7; ++b) o[136 + j * 7 + b] = aw1[b];
-            o[248 + j] = ab1;
+                for (int c = 0; c < 8; ++c) v[c] += d[c];
+            }
+            warp_transpose_reduce<32>(v, lane);
+            if (lane < 8) out[s * SCE_REC + 128 + lane] = v[0];
         }
     }
 }
@@ -778,77 +800,94 @@ struct HeadBwdArgs {
     int64_t P, chunk;
 };
 
-__global__ void __launch_bounds__(256) head_bwd_rows_kernel(const HeadBwdArgs a) {
-    __shared__ float s_head[241];
+constexpr int HEAD_RPT = 4;  // rows per thread: one pair of 128-bit weight reads per hidden unit serves all of them
+__global__ void __launch_bounds__(128) head_bwd_rows_kernel(const HeadBwdArgs a) {
+    __shared__ __align__(16) float s_head[241];
     const int g = blockIdx.y;
-    for (int i = threadIdx.x; i < 192; i += 256) s_head[i] = a.params[a.w1_off[g] + i];
+    for (int i = threadIdx.x; i < 192; i += 128) s_head[i] = a.params[a.w1_off[g] + i];
     if (threadIdx.x < 24) {
         s_head[192 + threadIdx.x] = a.params[a.b1_off[g] + threadIdx.x];
         s_head[216 + threadIdx.x] = a.params[a.w2_off[g] + threadIdx.x];
     }
     __syncthreads();
-    const int64_t row = blockIdx.x * 256ll + threadIdx.x;
-    if (row >= a.n_rows) return;
-    float c[8], dc[8];
-    load_row<8>(tptr(a.c, g, row), c);
-    const float dz = a.dz[g * a.n_rows + row];
+    int64_t row[HEAD_RPT];
+    float c[HEAD_RPT][8], dc[HEAD_RPT][8], dz[HEAD_RPT];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dc[i] = 0.f;
-#pragma unroll 4
-    for (int j = 0; j < 24; ++j) {
-        float h = s_head[192 + j];
+    for (int r = 0; r < HEAD_RPT; ++r) {
+        row[r] = blockIdx.x * (int64_t)(128 * HEAD_RPT) + r * 128 + threadIdx.x;
+        const bool live = row[r] < a.n_rows;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) h = fmaf(s_head[j * 8 + i], c[i], h);
-        const float dh = h > 0.f ? dz * s_head[216 + j] : 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) dc[i] = fmaf(s_head[j * 8 + i], dh, dc[i]);
+        for (int i = 0; i < 8; ++i) c[r][i] = 0.f, dc[r][i] = 0.f;
+        dz[r] = 0.f;
+        if (live) {
+            load_row<8>(tptr(a.c, g, row[r]), c[r]);
+            dz[r] = a.dz[g * a.n_rows + row[r]];
+        }
     }
-    store_row<8>(tptr(a.dc, g, row), dc);
+#pragma unroll 2
+    for (int j = 0; j < 24; ++j) {
+        float w[8];
+        load_row<8>(s_head + j * 8, w);
+        const float b1 = s_head[192 + j], w2 = s_head[216 + j];
+#pragma unroll
+        for (int r = 0; r < HEAD_RPT; ++r) {
+            float h = b1;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) h = fmaf(w[i], c[r][i], h);
+            const float dh = h > 0.f ? dz[r] * w2 : 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dc[r][i] = fmaf(w[i], dh, dc[r][i]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < HEAD_RPT; ++r)
+        if (row[r] < a.n_rows) store_row<8>(tptr(a.dc, g, row[r]), dc[r]);
 }
 
-// block 192 threads: j = tid>>3 (24 hidden units), sub = tid&7
-__global__ void __launch_bounds__(192) head_bwd_w_kernel(const HeadBwdArgs a) {
+// Weight gradients of MLP_k: warp w owns hidden units 3w .. 3w+2, LANE = ROW (coalesced loads of the saved conv
+// outputs and dz, lane-private sums, transposing butterfly at the end of the chunk).  Element order of the 32
+// per-warp sums: dW1[3][8], db1[3], dW2[3], db2 (warp 0 only), pad.
+__global__ void __launch_bounds__(256) head_bwd_w_kernel(const HeadBwdArgs a) {
     const int g = blockIdx.y;
-    const int j = threadIdx.x >> 3, sub = threadIdx.x & 7;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t r0 = blockIdx.x * a.chunk, r1 = min(r0 + a.chunk, a.n_rows);
-    float w1[8];
+    float w1[3][8], b1[3], w2[3];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) w1[i] = a.params[a.w1_off[g] + j * 8 + i];
-    const float b1 = a.params[a.b1_off[g] + j], w2 = a.params[a.w2_off[g] + j];
-    float aw1[8], ab1 = 0.f, aw2 = 0.f, ab2 = 0.f;
+    for (int jj = 0; jj < 3; ++jj) {
+        const int j = 3 * w + jj;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) aw1[i] = 0.f;
-    for (int64_t r = r0 + sub; r < r1; r += 8) {
+        for (int i = 0; i < 8; ++i) w1[jj][i] = a.params[a.w1_off[g] + j * 8 + i];
+        b1[jj] = a.params[a.b1_off[g] + j], w2[jj] = a.params[a.w2_off[g] + j];
+    }
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    const float *dzg = a.dz + g * a.n_rows;
+#pragma unroll 4
+    for (int64_t r = r0 + lane; r < r1; r += 32) {
         float c[8];
-        load_row<8>(tptr(a.c, g, r), c);
-        const float dz = a.dz[g * a.n_rows + r];
-        float h = b1;
+        gather_row<8>(tptr(a.c, g, r), c);
+        const float dz = dzg[r];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) h = fmaf(w1[i], c[i], h);
-        h = fmaxf(h, 0.f);
-        const float dh = h > 0.f ? dz * w2 : 0.f;
+        for (int jj = 0; jj < 3; ++jj) {
+            float h = b1[jj];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) aw1[i] = fmaf(dh, c[i], aw1[i]);
-        ab1 += dh;
-        aw2 = fmaf(dz, h, aw2);
-        ab2 += dz;
+            for (int i = 0; i < 8; ++i) h = fmaf(w1[jj][i], c[i], h);
+            h = fmaxf(h, 0.f);
+            const float dh = h > 0.f ? dz * w2[jj] : 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 * jj + i] = fmaf(dh, c[i], v[8 * jj + i]);
+            v[24 + jj] += dh;
+            v[27 + jj] = fmaf(dz, h, v[27 + jj]);
+        }
+        v[30] += dz;
     }
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) aw1[i] += __shfl_xor_sync(0xffffffffu, aw1[i], o);
-        ab1 += __shfl_xor_sync(0xffffffffu, ab1, o);
-        aw2 += __shfl_xor_sync(0xffffffffu, aw2, o);
-        ab2 += __shfl_xor_sync(0xffffffffu, ab2, o);
-    }
-    if (sub == 0) {
-        float *out = a.partial + blockIdx.x * a.P;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) out[a.w1_off[g] + j * 8 + i] = aw1[i];
-        out[a.b1_off[g] + j] = ab1;
-        out[a.w2_off[g] + j] = aw2;
-        if (j == 0) out[a.b2_off[g]] = ab2;
-    }
+    warp_transpose_reduce<32>(v, lane);
+    float *out = a.partial + blockIdx.x * a.P;
+    if (lane < 24) out[a.w1_off[g] + (3 * w + lane / 8) * 8 + (lane & 7)] = v[0];
+    else if (lane < 27) out[a.b1_off[g] + 3 * w + (lane - 24)] = v[0];
+    else if (lane < 30) out[a.w2_off[g] + 3 * w + (lane - 27)] = v[0];
+    else if (lane == 30 && w == 0) out[a.b2_off[g]] = v[0];
 }
 
 // dg[row][8] = sum over the 8 stages of dh_k[row][8] (h_k = g + LDFE_{k-1}: every stage feeds g), fixed order.
@@ -877,15 +916,28 @@ __global__ void finalize_grad_kernel(const float *__restrict__ partial, int64_t 
     grad[j] = t;
 }
 
-// SCE: reduce records over chunks, then expand the folded embedding terms (one block per scale).
-__global__ void __launch_bounds__(256) sce_finalize_kernel(const SceArgs a, const float *__restrict__ rec, int n_chunks,
-                                                           float *__restrict__ grad) {
+// SCE: reduce records over chunks, then expand the folded embedding terms (one block per scale).  A warp sums one
+// record element at a time: lanes stride over the chunks, then a fixed xor tree.
+__global__ void __launch_bounds__(1024) sce_finalize_kernel(const SceArgs a, const float *__restrict__ rec, int n_chunks,
+                                                            float *__restrict__ grad) {
     __shared__ float s_r[SCE_REC];
     const int s = blockIdx.x;
-    for (int i = threadIdx.x; i < SCE_REC; i += blockDim.x) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int i = w; i < SCE_REC; i += nw) {
         float t = 0.f;
-        for (int c = 0; c < n_chunks; ++c) t += rec[((int64_t)c * a.scale_num + s) * SCE_REC + i];
-        s_r[i] = t;
+        for (int c0 = lane; c0 < n_chunks; c0 += 32 * 8) {   // eight independent loads in flight, summed in order
+            float x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int c = c0 + 32 * u;
+                x[u] = c < n_chunks ? rec[((int64_t)c * a.scale_num + s) * SCE_REC + i] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t += x[u];
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) s_r[i] = t;
     }
     __syncthreads();
     const float *emb = a.params + a.emb_off + s * 8;

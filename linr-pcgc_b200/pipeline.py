@@ -98,6 +98,8 @@ class GopCoder:
     def __init__(self, device="cuda", bitdepth: int = 8, threads: Optional[int] = None):
         from concurrent.futures import ThreadPoolExecutor
         self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.bitdepth, self.threads = bitdepth, threads
         self.side = torch.cuda.Stream(self.device)
         self.pool = ThreadPoolExecutor(max_workers=1)
