@@ -169,6 +169,8 @@ __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
     }
 #pragma unroll 1
     for (int c = 0; c < 9; ++c) {
+        // (measured, round 1: loading the anchors one or two columns ahead, or prefetching the next column's
+        // neighbour rows into L2, does not pay -- the gathers themselves are the exposed latency)
         uint32_t m3[CONV_RPT];
         int nb[CONV_RPT];
         uint32_t any = 0;
@@ -463,24 +465,31 @@ __global__ void __launch_bounds__(BwdWCfg<CIN, COUT, MODE>::TPB) __maxnreg__((Bw
         }
     };
 
-    constexpr int D = Cfg::DEPTH;  // ring of D (neighbour row, dy row) buffers: loads run D-1 steps ahead of the FMAs
+    // Software pipeline over row steps (32 rows each): ring of D (neighbour row, dy row) buffers, loaded D-1 steps
+    // before their FMAs; the kernel-map words those loads need (mask, anchor) sit in their own ring and are loaded D
+    // steps before that, so no load is consumed less than ~2 steps after it was issued.
+    constexpr int D = Cfg::DEPTH;
     float xb[D][NK][XW];
     u64 db[D][HQ];
-    uint32_t mA;
-    int aA;
+    uint32_t mA[D];
+    int aA[D];
     int64_t r = r0 + lane;
 #pragma unroll
+    for (int u = 0; u < D; ++u) loadA(r + 32 * u, mA[u], aA[u]);
+#pragma unroll
     for (int u = 0; u < D - 1; ++u) {
-        loadA(r + 32 * u, mA, aA);
-        loadB(r + 32 * u, mA, aA, xb[u], db[u]);
+        loadB(r + 32 * u, mA[u], aA[u], xb[u], db[u]);
+        loadA(r + 32 * (u + D), mA[u], aA[u]);
     }
-    loadA(r + 32 * (D - 1), mA, aA);
 #pragma unroll 1
     for (; r - lane < r1; r += 32 * D) {  // warp-uniform trip count; rows past the chunk end contribute exact zeros
 #pragma unroll
         for (int u = 0; u < D; ++u) {
-            loadB(r + 32 * (u + D - 1), mA, aA, xb[(u + D - 1) % D], db[(u + D - 1) % D]);
-            loadA(r + 32 * (u + D), mA, aA);
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int v = (u + D - 1) % D;   // ring slot of step (current + D - 1)
+            loadB(r + 32 * (u + D - 1), mA[v], aA[v], xb[v], db[v]);
+            loadA(r + 32 * (u + 2 * D - 1), mA[v], aA[v]);
             fma(xb[u], db[u]);
         }
     }
