@@ -333,7 +333,10 @@ def main():
     achieved = (bytes_per_unit * d["units"]) / max(d["ms"], 1e-9) / 1e6 if d["launches"] else 0.0  # GB/s
     roofline = {"bound": "hbm", "kernel": d["kernel"], "achieved": achieved, "peak": peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "unit": "GB/s", "frac": achieved / peak,
+                "traffic": (NCU_DRAM_BYTES_PER_UNIT[d["kernel"]] * d["units"] / max(1, d["launches"])
+                            if d["kernel"] in NCU_DRAM_BYTES_PER_UNIT else None),
+                "traffic_source": "ncu --set full dram bytes per (row x group) unit, profiles/r01e_*, r01g_*; scaled by this run's units per launch",
                 "launches": d["launches"], "avg_launch_us": 1e3 * d["ms"] / max(1, d["launches"]),
                 "algorithmic_bytes_per_launch": bytes_per_unit * d["units"] / max(1, d["launches"]),
                 "mean_occupied_neighbours": pbar,
@@ -396,6 +399,17 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE 8-group launch over a loot-shaped frame (277,011 rows x 8 groups
+# = 2,216,088 units), from the `ncu --set full` captures summarised under profiles/ (r01e conv kernels, r01g weight
+# gradients); per unit, so it scales to the launches of this run.  None: not captured.
+NCU_DRAM_BYTES_PER_UNIT = {
+    "conv27<8,8>": (83.960832e6 + 39.300096e6) / 2216088, "conv27<8,4>": (82.984704e6 + 18.523136e6) / 2216088,
+    "conv27<4,4>": (173.155072e6 + 58.067968e6) / 2216088, "conv27_bits<8>": (11.316992e6 + 6.055936e6) / 1939077,
+    "conv27_head": (84.780544e6 + 47.52e6) / 2216088, "bwd_w<8,8>": (153.3184e6 + 8.76288e6) / 2216088,
+    "bwd_w<4,4>": (118.37824e6 + 4.628224e6) / 2216088, "bwd_w_bits<8>": (73.083136e6 + 3.748608e6) / 1939077,
+}
 
 
 def algorithmic_bytes(kernel: str, pbar: float) -> float:

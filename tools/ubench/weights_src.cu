@@ -224,6 +224,80 @@ void run_p(const float *x, const float *w, float *y, int n, const char *name) {
     printf("%-28s %8.1f us  %6.2f TFLOP/s (%4.1f%% of 74.4)  err=%s\n", name, ms * 1e3, 2 * macs / ms / 1e9, 2 * macs / ms / 1e9 / 74.4 * 100, cudaGetErrorString(cudaGetLastError()));
 }
 
+template <int RPT, int PAD_KB>
+__global__ void __launch_bounds__(128) kern_sp(const float *__restrict__ x, const float *__restrict__ wg, float *__restrict__ y, int n) {
+    extern __shared__ __align__(16) float s_all[];
+    float *s_w = s_all;
+    const int rows_s = 128 * RPT + 128;
+    float4 *s_x0 = reinterpret_cast<float4 *>(s_all + 27 * 64);
+    float4 *s_x1 = s_x0 + rows_s;
+    const int g = blockIdx.y;
+    for (int i = threadIdx.x; i < 27 * 64; i += 128) s_w[i] = wg[g * 27 * 64 + i];
+    const float *xg = x + (size_t)g * n * 8;
+    const int t0 = blockIdx.x * 128 * RPT - 64;
+    for (int i = threadIdx.x; i < rows_s * 2; i += 128) {
+        int rr = t0 + (i >> 1);
+        rr = rr < 0 ? 0 : (rr >= n ? n - 1 : rr);
+        const float4 v = reinterpret_cast<const float4 *>(xg + (size_t)rr * 8)[i & 1];
+        if (i & 1) s_x1[i >> 1] = v; else s_x0[i >> 1] = v;
+    }
+    __syncthreads();
+    int row[RPT];
+    u64 acc[RPT][4];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        row[r] = blockIdx.x * 128 * RPT + r * 128 + threadIdx.x;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[r][q] = 0;
+    }
+#pragma unroll 1
+    for (int k = 0; k < 27; ++k) {
+        float xv[RPT][8];
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int loc = row[r] + (k - 13) * 3 - t0;
+            const float4 a = s_x0[loc], b = s_x1[loc];
+            xv[r][0] = a.x, xv[r][1] = a.y, xv[r][2] = a.z, xv[r][3] = a.w, xv[r][4] = b.x, xv[r][5] = b.y, xv[r][6] = b.z, xv[r][7] = b.w;
+        }
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci) {
+            const ulonglong2 *w2 = reinterpret_cast<const ulonglong2 *>(s_w + k * 64 + ci * 8);
+            const ulonglong2 t0w = w2[0], t1w = w2[1];
+            u64 wq[4] = {t0w.x, t0w.y, t1w.x, t1w.y};
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                const u64 xx = pack2(xv[r][ci], xv[r][ci]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) ffma2_acc(acc[r][q], xx, wq[q]);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RPT; ++r)
+        if (row[r] < n)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) reinterpret_cast<u64 *>(y + ((size_t)g * n + row[r]) * 8)[q] = acc[r][q];
+}
+template <int RPT, int PAD_KB>
+void run_sp(const float *x, const float *w, float *y, int n, const char *name) {
+    dim3 grid((n + 128 * RPT - 1) / (128 * RPT), 8);
+    size_t smem = (size_t)PAD_KB * 1024;
+    cudaFuncSetAttribute(kern_sp<RPT, PAD_KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    for (int i = 0; i < 3; ++i) kern_sp<RPT, PAD_KB><<<grid, 128, smem>>>(x, w, y, n);
+    cudaEventRecord(e0);
+    const int it = 10;
+    for (int i = 0; i < it; ++i) kern_sp<RPT, PAD_KB><<<grid, 128, smem>>>(x, w, y, n);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms /= it;
+    double macs = (double)n * 8 * 27 * 64;
+    printf("%-28s %8.1f us  %6.2f TFLOP/s (%4.1f%% of 74.4)  err=%s\n", name, ms * 1e3, 2 * macs / ms / 1e9, 2 * macs / ms / 1e9 / 74.4 * 100, cudaGetErrorString(cudaGetLastError()));
+}
+
 int main() {
     const int n = 277000;
     float *x, *y, *w;
@@ -237,6 +311,10 @@ int main() {
     run<4, 0>(x, w, y, n, "smem  RPT=4");
     run_p<2>(x, w, y, n, "prefetch RPT=2");
     run_p<4>(x, w, y, n, "prefetch RPT=4");
+    run_sp<4, 32>(x, w, y, n, "planar staged RPT=4 32K(7blk)");
+    run_sp<4, 56>(x, w, y, n, "planar staged RPT=4 56K(4blk)");
+    run_sp<4, 75>(x, w, y, n, "planar staged RPT=4 75K(3blk)");
+    run_sp<8, 75>(x, w, y, n, "planar staged RPT=8 75K(3blk)");
     run_s<4, 32>(x, w, y, n, "staged RPT=4 smem32K(7blk)");
     run_s<4, 56>(x, w, y, n, "staged RPT=4 smem56K(4blk)");
     run_s<4, 75>(x, w, y, n, "staged RPT=4 smem75K(3blk)");
