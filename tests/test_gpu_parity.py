@@ -19,14 +19,14 @@ def L():
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
     import linr_pcgc_b200 as pkg
-    from linr_pcgc_b200 import _lib, codec, frame, net, rc, synth
+    from linr_pcgc_b200 import _lib, codec, frame, net, rc, synth, trainer
     _lib.load()  # raises if the extension is missing: there is no fallback
 
     class NS:
         pass
 
     ns = NS()
-    ns.frame, ns.net, ns.codec, ns.rc, ns.synth, ns.lib = frame, net, codec, rc, synth, _lib
+    ns.frame, ns.net, ns.codec, ns.rc, ns.synth, ns.lib, ns.trainer = frame, net, codec, rc, synth, _lib, trainer
     return ns
 
 
@@ -345,6 +345,30 @@ def test_full_size_encode_decode_lossless(L, O):
     run = L.net.NetRunner(S, fr.tables.n_rows, "cuda", train=False)
     all_bytes = L.codec.encode_frame(run, flat, fr)
     dec = L.codec.decode_frame(run, flat, all_bytes, fr.scale_coords(S - 1).contiguous())
+    assert dec.shape == fr.xyz.shape and (dec == fr.xyz).all()
+
+
+def test_owlii_sized_iteration_and_codec(L, O):
+    """Owlii-shaped frame (11-bit, ~2.5 M points, 8 scales, BASELINE.json configs[3]): two frame-iterations are
+    bitwise reproducible run to run (no floating-point atomics), the loss is finite, and the trained model codes the
+    frame losslessly at that size."""
+    import torch
+    pts = L.synth.make_sequence("owlii", 1, device="cuda")[0]
+    fr = L.frame.prepare_frame(pts, None, 64)
+    S = fr.n_scales
+    assert S == 8 and fr.point_num > 2_300_000
+    outs = []
+    for _ in range(2):
+        tr = L.trainer.GopTrainer(S, "cuda", seed=11, max_rows=fr.tables.n_rows)
+        b0 = float(tr.step(fr).item())
+        b1 = float(tr.step(fr).item())
+        assert b0 == b0 and b1 == b1 and 0 < b1 < 8.0 * 8 * fr.tables.n_rows
+        outs.append((b0, b1, tr.state.params.clone(), tr.grad.clone()))
+    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
+    assert torch.equal(outs[0][2], outs[1][2]) and torch.equal(outs[0][3], outs[1][3])
+    run = L.net.NetRunner(S, fr.tables.n_rows, "cuda", train=False)
+    all_bytes = L.codec.encode_frame(run, outs[0][2], fr)
+    dec = L.codec.decode_frame(run, outs[0][2], all_bytes, fr.scale_coords(S - 1).contiguous())
     assert dec.shape == fr.xyz.shape and (dec == fr.xyz).all()
 
 
