@@ -198,3 +198,34 @@ def test_world_size_2_gloo_state_broadcast_and_grad_allreduce():
     out = mgr.dict()
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+def test_me_shim_installs_and_refuses_cpu_tensors():
+    """linr_pcgc_b200.shim registers `MinkowskiEngine` / `torchac`; modules build on the host with the reference's
+    parameter shapes, but there is no CPU compute path."""
+    import importlib
+    import linr_pcgc_b200.shim as shim
+    saved = {k: sys.modules.get(k) for k in ("MinkowskiEngine", "torchac")}
+    try:
+        shim.install(force=True)
+        ME = importlib.import_module("MinkowskiEngine")
+        ta = importlib.import_module("torchac")
+        assert callable(ta.encode_float_cdf) and callable(ta.decode_float_cdf)
+        for name in ("SparseTensor", "MinkowskiConvolution", "MinkowskiReLU", "MinkowskiPruning", "cat", "utils"):
+            assert hasattr(ME, name), name
+        c3 = ME.MinkowskiConvolution(5, 8, kernel_size=3, stride=1, bias=True, dimension=3)
+        c1 = ME.MinkowskiConvolution(8, 4, kernel_size=1, stride=1, bias=True, dimension=3)
+        assert tuple(c3.kernel.shape) == (27, 5, 8) and tuple(c3.bias.shape) == (1, 8) and tuple(c1.kernel.shape) == (8, 4)
+        assert sorted(k for k, _ in c3.named_parameters()) == ["bias", "kernel"]
+        assert float(c3.kernel.abs().max()) <= 1.0 / np.sqrt(5 * 27) + 1e-7
+        xyz = torch.tensor([[0, 0, 0], [0, 0, 1], [1, 0, 0]], dtype=torch.int32)
+        C, F = ME.utils.sparse_collate([xyz], [torch.ones(3, 5)])
+        assert C.shape == (3, 4) and int(C[:, 0].abs().sum()) == 0 and torch.equal(C[:, 1:], xyz)
+        with pytest.raises(RuntimeError):
+            ME.SparseTensor(features=F, coordinates=C)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
