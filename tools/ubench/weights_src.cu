@@ -309,6 +309,8 @@ int main() {
     run<1, 0>(x, w, y, n, "smem  RPT=1");
     run<2, 0>(x, w, y, n, "smem  RPT=2");
     run<4, 0>(x, w, y, n, "smem  RPT=4");
+    run<8, 0>(x, w, y, n, "smem  RPT=8");
+    run<8, 1>(x, w, y, n, "const RPT=8");
     run_p<2>(x, w, y, n, "prefetch RPT=2");
     run_p<4>(x, w, y, n, "prefetch RPT=4");
     run_sp<4, 32>(x, w, y, n, "planar staged RPT=4 32K(7blk)");
