@@ -90,7 +90,7 @@ constexpr int CONV_TPB = 128;
 // conv; the 4-channel-input and bit-input convs are gather-bound and lose occupancy with more rows.
 template <int CIN, int COUT, int MODE>
 struct ConvCfg {
-    static constexpr int RPT = (CIN == 8 && MODE != 1) ? 4 : 2;
+    static constexpr int RPT = ((CIN == 8 && MODE != 1) || (CIN == 4 && COUT == 4)) ? 4 : 2;
     static constexpr int ROWS = CONV_TPB * RPT;  // rows per block
 };
 
