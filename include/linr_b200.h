@@ -154,6 +154,18 @@ int linr_net_decode_stage(const float *d_params, int scale_num, const linr_rows 
 /* Scatter one decoded stage back into the occupancy bytes: occ[row] |= sym[row] << stage. */
 int linr_occ_set_stage(uint8_t *d_occ, const uint8_t *d_sym, int64_t n_rows, int stage, void *stream);
 
+/* One whole scale of the sequential decoder in ONE call (CNP.decode, models/upsample.py:249-295, driven per scale by
+ * decode_one_frame, decoder.py:153-176): _begin, then for k = 0..7: _stage k -> CDF midpoints to the host -> range
+ * decoder on stream k (torchac.decode_float_cdf, models/module_utils.py:38) -> symbols back to the device ->
+ * occ |= sym << k.  The eight device<->host round trips happen inside the call (it synchronises `stream` eight
+ * times), so a host thread per frame keeps a GPU stream busy without holding an interpreter lock.
+ *  h_streams[8] / h_nbytes[8]: the stage bitstreams (unpack_bitstream, models/function_utils.py:119-132)
+ *  d_cdf u16[n_rows], d_sym u8[n_rows]: device scratch;  h_cdf u16[n_rows], h_sym u8[n_rows]: PINNED host scratch
+ *  rows->d_occ: zero-filled by the caller, holds the decoded 8-bit occupancy on return. */
+int linr_net_decode_scale(const float *d_params, int scale_num, const linr_rows *rows, const uint8_t *const *h_streams,
+                          const int64_t *h_nbytes, uint16_t *d_cdf, uint8_t *d_sym, uint16_t *h_cdf, uint8_t *h_sym,
+                          void *d_ws, size_t ws_bytes, void *stream);
+
 /* Single-layer entry points (used by the MinkowskiEngine-shaped shim and by unit tests).
  * ME.MinkowskiConvolution(kernel_size=3, stride=1) forward on one coordinate set (models/upsample.py:17,90,95):
  *   y[n,cout] = sum_k x[row(C+delta_k)] @ W[k] + bias;  W [27,cin,cout], bias [cout] or NULL; cin,cout in {4,8}. */

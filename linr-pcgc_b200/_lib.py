@@ -53,6 +53,7 @@ SIGNATURES = {
     "linr_net_decode_begin": (_I, [_P, _I, _RP, _P, _SZ, _P]),
     "linr_net_decode_stage": (_I, [_P, _I, _RP, _I, _P, _P, _P, _SZ, _P]),
     "linr_occ_set_stage": (_I, [_P, _P, _I64, _I, _P]),
+    "linr_net_decode_scale": (_I, [_P, _I, _RP, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "linr_spconv27_fwd": (_I, [_P, _I, _P, _P, _P, _I, _RP, _I, _P]),
     "linr_spconv27_bwd_in": (_I, [_P, _I, _P, _P, _I, _RP, _P]),
     "linr_spconv27_bwd_w_ws_bytes": (_SZ, [_I64, _I, _I]),

@@ -160,17 +160,10 @@ def decode_scale(runner: NetRunner, params: torch.Tensor, coords: torch.Tensor, 
     occ = torch.zeros(n, dtype=torch.uint8, device=dev)
     t = build_tables(coords, scale, occ)
     streams = unpack_bitstream(data)
-    runner.decode_begin(params, t)
-    h_cdf, h_sym = ctx.h_cdf[:n], ctx.h_sym[:n]
     d_sym = torch.empty(n, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream()
-    for k in range(8):
-        d_cdf, _ = runner.decode_stage(params, t, k)
-        h_cdf.copy_(d_cdf, non_blocking=True)
-        stream.synchronize()
-        rc.decode_binary_into(h_cdf.numpy().view(np.uint16), streams[k], h_sym.numpy())
-        d_sym.copy_(h_sym, non_blocking=True)
-        runner.occ_set_stage(occ, d_sym, k)
+    # the eight device<->host round trips of the scale run inside one C call (no interpreter lock held), so the frames
+    # decoded by other host threads overlap with this one
+    runner.decode_scale(params, t, streams, d_sym, ctx.h_cdf, ctx.h_sym)
     return occ, t
 
 

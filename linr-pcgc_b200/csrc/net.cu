@@ -705,6 +705,32 @@ int linr_occ_set_stage(uint8_t *d_occ, const uint8_t *d_sym, int64_t n_rows, int
     return LINR_OK;
 }
 
+int linr_net_decode_scale(const float *d_params, int scale_num, const linr_rows *rows, const uint8_t *const *h_streams,
+                          const int64_t *h_nbytes, uint16_t *d_cdf, uint8_t *d_sym, uint16_t *h_cdf, uint8_t *h_sym,
+                          void *d_ws, size_t ws_bytes, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = check_rows(rows, scale_num, true);
+    if (rc) return rc;
+    const int64_t n = rows->n_rows;
+    if (n == 0) return LINR_OK;
+    LINR_REQUIRE(h_streams && h_nbytes && d_cdf && d_sym && h_cdf && h_sym, "linr_net_decode_scale: null buffer");
+    rc = linr_net_decode_begin(d_params, scale_num, rows, d_ws, ws_bytes, stream);
+    if (rc) return rc;
+    for (int k = 0; k < 8; ++k) {
+        rc = linr_net_decode_stage(d_params, scale_num, rows, k, nullptr, d_cdf, d_ws, ws_bytes, stream);
+        if (rc) return rc;
+        LINR_CHECK_CUDA(cudaMemcpyAsync(h_cdf, d_cdf, sizeof(uint16_t) * n, cudaMemcpyDeviceToHost, s));
+        LINR_CHECK_CUDA(cudaStreamSynchronize(s));
+        rc = linr_rc_decode_binary(h_cdf, h_streams[k], h_nbytes[k], h_sym, n);
+        if (rc) return rc;
+        // h_sym is rewritten only after the next stage's synchronise, which follows this copy in stream order
+        LINR_CHECK_CUDA(cudaMemcpyAsync(d_sym, h_sym, (size_t)n, cudaMemcpyHostToDevice, s));
+        rc = linr_occ_set_stage(const_cast<uint8_t *>(rows->d_occ), d_sym, n, k, stream);
+        if (rc) return rc;
+    }
+    return LINR_OK;
+}
+
 // ---- single-layer entry points ---------------------------------------------------------------------------
 static int conv_dims_ok(int cin, int cout) { return (cin == 4 || cin == 8) && (cout == 4 || cout == 8); }
 

@@ -8,6 +8,7 @@ from __future__ import annotations
 import ctypes as C
 from typing import Optional
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -88,6 +89,21 @@ class NetRunner:
                                              ptr(self.probs) if want_probs else None, ptr(self.cdf), ptr(self.ws),
                                              self.ws.numel(), stream_ptr()), "linr_net_decode_stage")
         return self.cdf[:n], (self.probs[:n] if want_probs else None)
+
+    def decode_scale(self, params: torch.Tensor, t: RowTables, streams, d_sym: torch.Tensor, h_cdf: torch.Tensor,
+                     h_sym: torch.Tensor):
+        """The 8 sequential stages of one scale in one C call (linr_net_decode_scale): t.occ must be zero-filled and
+        holds the decoded occupancy afterwards; h_cdf / h_sym are pinned host scratch of >= n_rows elements."""
+        n = t.n_rows
+        assert len(streams) == 8 and h_cdf.is_pinned() and h_sym.is_pinned() and h_cdf.numel() >= n and h_sym.numel() >= n
+        self.reserve(n)
+        bufs = [np.frombuffer(b, dtype=np.uint8) if len(b) else np.zeros(1, np.uint8) for b in streams]
+        ptrs = (C.c_void_p * 8)(*[b.ctypes.data for b in bufs])
+        lens = (C.c_int64 * 8)(*[len(b) for b in streams])
+        rows = t.rows()
+        check(self.lib.linr_net_decode_scale(ptr(params), self.S, C.byref(rows), ptrs, lens, ptr(self.cdf), ptr(d_sym),
+                                             h_cdf.data_ptr(), h_sym.data_ptr(), ptr(self.ws), self.ws.numel(), stream_ptr()),
+              "linr_net_decode_scale")
 
     def occ_set_stage(self, occ: torch.Tensor, sym: torch.Tensor, stage: int):
         check(self.lib.linr_occ_set_stage(ptr(occ), ptr(sym), int(occ.numel()), stage, stream_ptr()), "linr_occ_set_stage")
