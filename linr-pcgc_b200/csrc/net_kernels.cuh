@@ -4,8 +4,9 @@
 // fixed (offset column c = 0..8, then dz = -1,0,+1, then input channel) and does not depend on the
 // grid, on grouping or on which stage/scale is being processed -> encoder (batched, teacher forced)
 // and decoder (sequential) produce bit-identical probabilities.
-// Weight gradients: block partial sums in registers, warp-shuffle tree, one partial vector per row
-// chunk, summed later in chunk order (no floating-point atomics anywhere).
+// Weight gradients (conv, MLP heads, SCE): LANE = ROW with lane-private sums over a row chunk, one
+// transposing warp butterfly per chunk, one partial vector per chunk, summed later in chunk order
+// (no floating-point atomics anywhere -> bitwise reproducible run to run).
 #pragma once
 #include "common.cuh"
 
@@ -485,8 +486,6 @@ __global__ void __launch_bounds__(BwdWCfg<CIN, COUT, MODE>::TPB) __maxnreg__((Bw
     for (; r - lane < r1; r += 32 * D) {  // warp-uniform trip count; rows past the chunk end contribute exact zeros
 #pragma unroll
         for (int u = 0; u < D; ++u) {
-            constexpr int dummy = 0;
-            (void)dummy;
             const int v = (u + D - 1) % D;   // ring slot of step (current + D - 1)
             loadB(r + 32 * (u + D - 1), mA[v], aA[v], xb[v], db[v]);
             loadA(r + 32 * (u + 2 * D - 1), mA[v], aA[v]);
