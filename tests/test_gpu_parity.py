@@ -348,6 +348,48 @@ def test_full_size_encode_decode_lossless(L, O):
     assert dec.shape == fr.xyz.shape and (dec == fr.xyz).all()
 
 
+def test_gop_overfit_tracks_oracle_training_and_bpp(L, O):
+    """The north star's end criterion on a small GOP: the same overfitting schedule (one Adam step per frame,
+    StepLR per step, main.py:297-322) run by the CPU oracle and by the CUDA path from the same initial parameters gives
+    the same loss curve (1e-3 relative after 8 optimiser steps) and bitstreams within 0.5 % of each other in size."""
+    import torch
+    from linr_pcgc_b200 import params as P
+    pts = L.synth.make_sequence("tiny", 2)
+    frames = [L.frame.prepare_frame(p.cuda(), None, 64) for p in pts]
+    S = frames[0].n_scales
+    flat0 = P.init_flat(S, seed=13)
+    # ---- oracle: 4 epochs x 2 frames
+    ofr = [O.prepare_frame(p.numpy(), S, 64) for p in pts]
+    nbrs = [[torch.from_numpy(O.nbr27(sc["coord"]).astype(np.int64)) for sc in f["scales"]] for f in ofr]
+    flat = flat0.clone()
+    m, v = torch.zeros_like(flat), torch.zeros_like(flat)
+    ref_losses, step = [], 0
+    for ep in range(4):
+        acc = []
+        for f, nb in zip(ofr, nbrs):
+            p = flat.clone().requires_grad_(True)
+            bits = O.frame_bits(O.unflatten_params(p, S), f, nb)
+            (bits / f["point_num"]).backward()
+            step += 1
+            with torch.no_grad():
+                O.adam_step_reference([flat], [p.grad], [m], [v], step=step, lr=O.lr_at_step(step - 1))
+            acc.append(float(bits.detach()) / f["point_num"])
+        ref_losses.append(float(np.mean(acc)))
+    with torch.no_grad():
+        ref_bytes = sum(len(b) for f in ofr for b in O.encode_frame(O.unflatten_params(flat, S), f))
+    # ---- CUDA path
+    tr = L.trainer.GopTrainer(S, "cuda", max_rows=max(f.tables.n_rows for f in frames),
+                              state=L.trainer.OptimState(flat0.clone().cuda(), torch.zeros_like(flat0).cuda(),
+                                                         torch.zeros_like(flat0).cuda(), 0, 0, 0.01))
+    losses = tr.fit(frames, 4)
+    np.testing.assert_allclose(losses, ref_losses, rtol=1e-3)
+    assert losses[-1] < losses[0]
+    run = L.net.NetRunner(S, max(f.tables.n_rows for f in frames), "cuda", train=False)
+    got_bytes = sum(len(b) for f in frames for b in L.codec.encode_frame(run, tr.state.params, f))
+    assert abs(got_bytes - ref_bytes) <= 0.005 * ref_bytes, (got_bytes, ref_bytes)
+    np.testing.assert_allclose(tr.state.params.cpu().numpy(), flat.numpy(), rtol=0, atol=2e-3)
+
+
 def test_owlii_sized_iteration_and_codec(L, O):
     """Owlii-shaped frame (11-bit, ~2.5 M points, 8 scales, BASELINE.json configs[3]): two frame-iterations are
     bitwise reproducible run to run (no floating-point atomics), the loss is finite, and the trained model codes the
