@@ -185,13 +185,17 @@ def run_reference(args):
 
 
 def workload_config(args, n):
-    return {"workload": f"{args.shape}-shaped synthetic 10-bit surface, ~780k pts/frame, gop_size {args.frames}, "
-                        f"{args.epochs} epochs/GOP, overfit + model quantisation + encode (BASELINE.json configs[1])",
+    from linr_pcgc_b200 import synth
+    bits, pts = synth.SHAPES[args.shape]
+    cfg = {"loot": "BASELINE.json configs[1]", "owlii": "BASELINE.json configs[3] (per-GPU share)",
+           "plumbing": "BASELINE.json configs[0]"}.get(args.shape, "parity-test shape")
+    return {"workload": f"{args.shape}-shaped synthetic {bits}-bit surface, ~{pts // 1000}k pts/frame, gop_size {args.frames}, "
+                        f"{args.epochs} epochs/GOP, overfit + model quantisation + encode ({cfg})",
             "gop_size": args.frames, "epochs": args.epochs, "frames_per_step": args.frames * (1 if args.dp else n),
             "parallelism": ("dp%d (frames of one GOP split, NCCL all-reduce of gradients)" % n) if args.dp and n > 1
             else ("gop%d (one GOP per GPU, no collective)" % n),
             "gop_pipeline": "coding of GOP i overlaps overfitting of GOP i+1 (all K GOPs coded inside the timed region)" if args.gop_pipeline else "serial",
-            "l2_policy": "inputs larger than L2: one GOP's resident tables + activations ~1.3 GB >> 126 MB L2"}
+            "l2_policy": "inputs larger than L2: one GOP's resident tables + activations >> 126 MB L2"}
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
