@@ -79,6 +79,33 @@ struct Coder {
             high = (high << 1) | 1u;
         }
     }
+    // Binary alphabet {[0,m), [m,2^16)}: one multiply; the renormalisation loop is entered only when a bit can leave
+    // (same interval arithmetic as narrow(): sym 1 -> low += t, sym 0 -> high = low + t - 1, t = span*m >> 16).
+    inline void narrow_binary(uint32_t m, unsigned sym, BitWriter &w) {
+        const uint64_t span = (uint64_t)high - (uint64_t)low + 1;
+        const uint32_t t = (uint32_t)((span * (uint64_t)m) >> 16);
+        const uint32_t bound = low + t;
+        const uint32_t sel = 0u - (uint32_t)(sym & 1u);      // branch-free select
+        low = (bound & sel) | (low & ~sel);
+        high = (high & sel) | ((bound - 1u) & ~sel);
+        if ((((low ^ high) & 0x80000000u) != 0u) && !(low >= 0x40000000u && high < 0xC0000000u)) return;
+        for (;;) {
+            if (high < 0x80000000u) {
+                w.put_with_pending(0, pending);
+            } else if (low >= 0x80000000u) {
+                w.put_with_pending(1, pending);
+            } else if (low >= 0x40000000u && high < 0xC0000000u) {
+                ++pending;
+                low = (low << 1) & 0x7FFFFFFFu;
+                high = (high << 1) | 0x80000001u;
+                continue;
+            } else {
+                break;
+            }
+            low <<= 1;
+            high = (high << 1) | 1u;
+        }
+    }
     inline void flush(BitWriter &w) {
         pending += 1;
         w.put_with_pending(low < 0x40000000u ? 0u : 1u, pending);
@@ -102,6 +129,31 @@ struct BitReader {
         }
         value = (value << 1) | ((cache >> (cached - 1)) & 1u);
         --cached;
+    }
+};
+
+// MSB-first reader with a 64-bit window: take(n) returns the next n (1..32) bits, zeros past the end (torchac pads
+// the tail with zero bits).
+struct BitWindow {
+    const uint8_t *in;
+    int64_t n, pos = 0;
+    uint64_t buf = 0;
+    int have = 0;
+    BitWindow(const uint8_t *p, int64_t nb) : in(p), n(nb) {}
+    inline void refill() {
+        while (have <= 56) {
+            const uint64_t byte = pos < n ? in[pos] : 0u;
+            ++pos;
+            buf |= byte << (56 - have);
+            have += 8;
+        }
+    }
+    inline uint32_t take(int k) {
+        if (have < k) refill();
+        const uint32_t v = (uint32_t)(buf >> (64 - k));
+        buf <<= k;
+        have -= k;
+        return v;
     }
 };
 
@@ -134,9 +186,7 @@ int64_t encode_binary(const uint16_t *mid, const uint8_t *sym, int shift, int64_
     BitWriter w(out, cap);
     Coder c;
     for (int64_t i = 0; i < n; ++i) {
-        const uint32_t m = mid[i];
-        if ((sym[i] >> shift) & 1u) c.narrow(m, 0x10000u, w);
-        else c.narrow(0u, m, w);
+        c.narrow_binary(mid[i], (sym[i] >> shift) & 1u, w);
     }
     c.flush(w);
     return w.finish();
@@ -152,19 +202,41 @@ int64_t linr_rc_encode_binary(const uint16_t *h_cdf_mid, const uint8_t *h_sym, i
 }
 
 int linr_rc_decode_binary(const uint16_t *h_cdf_mid, const uint8_t *h_in, int64_t nbytes, uint8_t *h_sym, int64_t n) {
-    BitReader r(h_in, nbytes);
-    Decoder d;
-    d.prime(r);
+    BitWindow r(h_in, nbytes);
+    uint32_t low = 0, high = 0xFFFFFFFFu, value = r.take(32);
     for (int64_t i = 0; i < n; ++i) {
-        const uint64_t span = (uint64_t)d.high - (uint64_t)d.low + 1;
-        const uint32_t m = h_cdf_mid[i];
         // torchac: count = ((value-low+1)*2^16 - 1) / span; sym = (count >= mid)  <=>  (value-low+1)*2^16 > mid*span
-        const uint64_t a = ((uint64_t)d.value - (uint64_t)d.low + 1) << 16;
-        const unsigned s = a > (uint64_t)m * span ? 1u : 0u;
+        // <=> value - low >= t with t = mid*span >> 16, which is also the interval split -> one multiply per symbol
+        const uint64_t span = (uint64_t)high - (uint64_t)low + 1;
+        const uint32_t t = (uint32_t)((span * (uint64_t)h_cdf_mid[i]) >> 16);
+        const uint32_t bound = low + t;
+        const uint32_t s = value >= bound ? 1u : 0u;      // value, bound in [low, high]: no wrap
         h_sym[i] = (uint8_t)s;
         if (i == n - 1) break;
-        if (s) d.narrow(m, 0x10000u, span, r);
-        else d.narrow(0u, m, span, r);
+        const uint32_t sel = 0u - s;                       // branch-free select: the symbol is not predictable
+        low = (bound & sel) | (low & ~sel);
+        high = (high & sel) | ((bound - 1u) & ~sel);
+        // renormalise: all leading bits low and high share leave at once (the bit-by-bit loop would take them one after
+        // the other before it ever looks at the underflow case), then the underflow (E3) steps, and again
+        for (;;) {
+            const uint32_t diff = low ^ high;
+            if ((diff & 0x80000000u) == 0u) {
+                const int k = diff ? __builtin_clz(diff) : 32;
+                if (k == 32) {
+                    low = 0u, high = 0xFFFFFFFFu, value = r.take(32);
+                } else {
+                    low <<= k;
+                    high = (high << k) | ((1u << k) - 1u);
+                    value = (value << k) | r.take(k);
+                }
+            } else if (low >= 0x40000000u && high < 0xC0000000u) {
+                low = (low << 1) & 0x7FFFFFFFu;
+                high = (high << 1) | 0x80000001u;
+                value = ((value - 0x40000000u) << 1) | r.take(1);
+            } else {
+                break;
+            }
+        }
     }
     return LINR_OK;
 }
