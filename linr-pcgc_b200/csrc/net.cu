@@ -3,6 +3,7 @@
 // caller's stream; nothing here synchronises.  Mirrors (does not copy) the structure of
 // models/model_core.py:38-81, models/upsample.py:137-295 and models/resnet.py:55-60 of the reference.
 #include <math.h>
+#include <stdlib.h>
 #include <stdarg.h>
 
 #include <mutex>
@@ -107,6 +108,11 @@ struct Layout {
     int conv_first = 0;  // first parameter that is not SCE (embedding + scale MLPs)
     int total = 0;
     std::vector<int64_t> offsets;  // one per tensor, parameters() order
+    // weight bank plan (net_kernels.cuh): fills 0..3 serve the forward launches, 4..7 the grad-input launches
+    std::vector<BankItem> bank;
+    int fill_len[8] = {0};
+    int fill_base[8] = {0};
+    int stage_floats = 0;
 };
 
 // parameters() order of LINR_PCGC_Model (checkpoint contract)
@@ -148,6 +154,28 @@ Layout make_layout(int S) {
     for (int k = 0; k < 7; ++k) L.blk8[k] = L.ob[k];
     L.blk8[7] = L.bin;
     L.total = o;
+    // ---- weight bank plan: every fill <= BANK_FLOATS, items in launch order
+    auto add = [&](int fill, int w_off, int flip, int cin, int cout) {
+        L.bank.push_back(BankItem{w_off, flip, cin, cout, fill, L.fill_len[fill]});
+        L.fill_len[fill] += 27 * cin * cout;
+    };
+    add(0, L.bin.A_w, 0, 8, 8);   // forward: ConvA of GDFE (the bit-input ConvA of the LDFE blocks is faster from shared memory)
+    for (int g = 0; g < 8; ++g) add(1, L.blk8[g].c00_w, 0, 8, 4);        // the three 27-offset inner layers
+    for (int g = 0; g < 8; ++g) add(1, L.blk8[g].c01_w, 0, 4, 4);
+    for (int g = 0; g < 8; ++g) add(1, L.blk8[g].c11_w, 0, 4, 4);
+    add(2, L.bin.B_w, 0, 8, 8);                                        // ConvB
+    for (int g = 0; g < 7; ++g) add(2, L.ob[g].B_w, 0, 8, 8);
+    for (int k = 0; k < 8; ++k) add(3, L.pr_w[k], 0, 8, 8);            // SConv_k of the heads
+    for (int k = 0; k < 8; ++k) add(4, L.pr_w[k], 1, 8, 8);            // backward: grad-input layouts
+    for (int g = 0; g < 8; ++g) add(5, L.blk8[g].B_w, 1, 8, 8);
+    for (int g = 0; g < 8; ++g) add(6, L.blk8[g].c01_w, 1, 4, 4);
+    for (int g = 0; g < 8; ++g) add(6, L.blk8[g].c00_w, 1, 4, 8);        // launch<4,8>: dt0 (4) -> dy (8)
+    for (int g = 0; g < 8; ++g) add(6, L.blk8[g].c11_w, 1, 4, 4);
+    add(7, L.bin.A_w, 1, 8, 8);
+    for (int f = 0; f < 8; ++f) {
+        L.fill_base[f] = L.stage_floats;
+        L.stage_floats += (L.fill_len[f] + 63) / 64 * 64;
+    }
     return L;
 }
 
@@ -172,6 +200,7 @@ struct NetWs {
     // backward
     float *dc, *dhh, *dg, *g_dz, *g_dt0, *g_dy, *g_dt2, *g_dt1, *df0;
     float *partial, *sce_rec;
+    float *stage;  // weight-bank staging (train only)
     bool ok = false;
     size_t used = 0;
 };
@@ -209,6 +238,7 @@ NetWs carve_net(void *ws, size_t bytes, int64_t R, int train, int P, int S) {
         w.df0 = c.take<float>(r * 8);
         w.partial = c.take<float>((size_t)w.n_chunks * P);
         w.sce_rec = c.take<float>((size_t)w.n_chunks * S * SCE_REC);
+        w.stage = c.take<float>(8 * (size_t)BANK_FLOATS);
     }
     w.ok = c.ok;
     w.used = c.off;
@@ -221,11 +251,86 @@ inline Tens TN() { return Tens{nullptr, 0, 0, 0}; }
 
 RowMap map_of(const linr_rows *r) { return RowMap{r->d_anchor, r->ld, r->d_mask, r->n_rows}; }
 
+// ---- weight bank (constant memory is one per process: a single stream owns it, everybody else uses shared memory)
+struct BankOwner {
+    std::mutex mu;
+    bool owned = false;
+    cudaStream_t stream = nullptr;
+    int device = -1;
+} g_bank_owner;
+
+bool bank_claim(cudaStream_t s) {
+    static const bool disabled = getenv("LINR_NO_WEIGHT_BANK") != nullptr;
+    if (disabled) return false;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(g_bank_owner.mu);
+    if (!g_bank_owner.owned) {
+        g_bank_owner.owned = true, g_bank_owner.stream = s, g_bank_owner.device = dev;
+        return true;
+    }
+    return g_bank_owner.stream == s && g_bank_owner.device == dev;
+}
+
+struct BankCtx {   // lives for one linr_net_forward(train) / linr_net_backward call on the owning stream
+    const Layout *L;
+    float *stage;
+    int cur_fill;
+};
+thread_local BankCtx *t_bank = nullptr;
+
+// Stage the items of fills [f0, f1) of this call's parameters; returns false (and leaves the bank path off) if the
+// caller's stream does not own the bank.
+bool bank_begin(BankCtx &ctx, const Layout &L, const float *params, float *stage, int f0, int f1, cudaStream_t s) {
+    if (!stage || !bank_claim(s)) return false;
+    BankItems items;
+    items.n = 0;
+    for (int f = 0; f < 8; ++f) items.fill_base[f] = L.fill_base[f];
+    for (int f = 8; f < 16; ++f) items.fill_base[f] = 0;
+    for (const BankItem &it : L.bank)
+        if (it.fill >= f0 && it.fill < f1 && items.n < BANK_MAX_ITEMS) items.it[items.n++] = it;
+    ProfScope prof(K_REDUCE, items.n, s);
+    bank_stage_kernel<<<items.n, 256, 0, s>>>(params, items, stage);
+    ctx.L = &L, ctx.stage = stage, ctx.cur_fill = -1;
+    t_bank = &ctx;
+    return true;
+}
+struct BankScope {
+    ~BankScope() { t_bank = nullptr; }
+};
+
 template <int CIN, int COUT, int MODE>
 void launch_conv(const ConvArgs &a, int G, cudaStream_t s) {
     if (a.map.n_rows <= 0) return;
-    dim3 grid((unsigned)ceil_div64(a.map.n_rows, (ConvCfg<CIN, COUT, MODE>::ROWS)), (unsigned)G);
     constexpr int cls = MODE == 2 ? K_CONVHEAD : MODE == 1 ? K_CONVBITS : (CIN == 8 ? (COUT == 8 ? K_CONV88 : K_CONV84) : (COUT == 8 ? K_CONV48 : K_CONV44));
+    if (MODE != 1 && t_bank && !a.bias_direct) {
+        // every group's weights must sit in ONE fill of the plan; otherwise this launch stays on shared memory
+        ConvArgs b = a;
+        int fill = -1;
+        bool ok = true;
+        for (int g = 0; g < G && ok; ++g) {
+            const BankItem *hit = nullptr;
+            for (const BankItem &it : t_bank->L->bank)
+                if (it.w_off == a.w_off[g] && it.flip == (a.flip ? 1 : 0)) {
+                    hit = &it;
+                    break;
+                }
+            if (!hit || (fill >= 0 && hit->fill != fill)) ok = false;
+            else fill = hit->fill, b.bank_off[g] = hit->dst;
+        }
+        if (ok) {
+            if (t_bank->cur_fill != fill) {
+                cudaMemcpyToSymbolAsync(c_bank, t_bank->stage + t_bank->L->fill_base[fill], sizeof(float) * t_bank->L->fill_len[fill],
+                                        0, cudaMemcpyDeviceToDevice, s);
+                t_bank->cur_fill = fill;
+            }
+            dim3 grid((unsigned)ceil_div64(a.map.n_rows, (ConvCfg<CIN, COUT, MODE, true>::ROWS)), (unsigned)G);
+            ProfScope prof(cls, a.map.n_rows * G, s);
+            conv27_kernel<CIN, COUT, MODE, true><<<grid, CONV_TPB, 0, s>>>(b);
+            return;
+        }
+    }
+    dim3 grid((unsigned)ceil_div64(a.map.n_rows, (ConvCfg<CIN, COUT, MODE>::ROWS)), (unsigned)G);
     ProfScope prof(cls, a.map.n_rows * G, s);
     conv27_kernel<CIN, COUT, MODE><<<grid, CONV_TPB, 0, s>>>(a);
 }
@@ -545,6 +650,9 @@ int linr_net_forward(const float *d_params, int scale_num, const linr_rows *rows
         return LINR_OK;
     }
     const RowMap m = map_of(rows);
+    BankCtx bank_ctx;
+    BankScope bank_scope;
+    if (train) bank_begin(bank_ctx, L, d_params, w.stage, 0, 4, s);   // training forward: weights via the constant bank
     {  // SCE
         SceArgs a = sce_args(d_params, L, rows);
         a.f0 = T(w.f0, 0, 8);
@@ -590,6 +698,9 @@ int linr_net_backward(const float *d_params, int scale_num, const linr_rows *row
         return LINR_OK;
     }
     const RowMap m = map_of(rows);
+    BankCtx bank_ctx;
+    BankScope bank_scope;
+    bank_begin(bank_ctx, L, d_params, w.stage, 4, 8, s);
     // heads: dc, MLP weight partials, SConv weight partials, dh_k
     {
         HeadBwdArgs a;

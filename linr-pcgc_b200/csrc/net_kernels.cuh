@@ -83,17 +83,27 @@ struct ConvArgs {
     float dz_scale;       // loss_scale / ln2
     float *bits_partial;  // [gridDim.y * gridDim.x] or null
     int64_t out_ld;       // row count used as the stage stride of probs/cdf/dz
+    int bank_off[MAXG];   // CW variant: float offset of each group's staged weights in the constant bank
 };
 
 constexpr int CONV_TPB = 128;
 // rows per thread: the weights of an offset are read from shared memory once for all of them (the L1/shared
 // wavefront pipe, not the FMA pipe, is what saturates first).  Measured (round 1): 4 rows help every 8-channel-input
 // conv; the 4-channel-input and bit-input convs are gather-bound and lose occupancy with more rows.
-template <int CIN, int COUT, int MODE>
+template <int CIN, int COUT, int MODE, bool CW = false>
 struct ConvCfg {
-    static constexpr int RPT = ((CIN == 8 && MODE != 1) || (CIN == 4 && COUT == 4)) ? 4 : 2;
+    // constant-bank weights cost issue slots of the uniform datapath instead of L1 wavefronts: always 4 rows
+    static constexpr int RPT = (CW || (CIN == 8 && MODE != 1) || (CIN == 4 && COUT == 4)) ? 4 : 2;
     static constexpr int ROWS = CONV_TPB * RPT;  // rows per block
 };
+
+// Weight bank: the weights of the conv launches of one training call, staged per "fill" (<= 62 KB) into the constant
+// bank by cudaMemcpyToSymbolAsync, so that the CW kernel variant reads them as uniform-register FFMA2 operands
+// (LDCU) -- no shared-memory broadcasts, which share the L1 data pipe with the gathers (-15 % on the
+// 8->8 forward).  One stream per process owns the bank (net.cu); every other caller runs the shared-memory variant,
+// which computes the same bits.
+constexpr int BANK_FLOATS = 15872;
+__constant__ __align__(16) float c_bank[BANK_FLOATS];
 
 // Packed fp32x2 FMA (Blackwell FFMA2): two independent IEEE fp32 FMAs per instruction, so results are bit-identical
 // to scalar fmaf; `pack2(x, x)` compiles to the scalar-broadcast operand form (no extra moves).
@@ -119,11 +129,11 @@ __device__ __forceinline__ u64 fadd2(u64 a, u64 b) {
     return d;
 }
 
-template <int CIN, int COUT, int MODE>
+template <int CIN, int COUT, int MODE, bool CW = false>
 __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
-    constexpr int WMAX = (MODE == 1) ? 27 * 7 * COUT : 27 * CIN * COUT;
+    constexpr int WMAX = CW ? 4 : ((MODE == 1) ? 27 * 7 * COUT : 27 * CIN * COUT);
     constexpr int HQ = COUT / 2;  // accumulator pairs per row
-    constexpr int CONV_RPT = ConvCfg<CIN, COUT, MODE>::RPT, CONV_ROWS = ConvCfg<CIN, COUT, MODE>::ROWS;
+    constexpr int CONV_RPT = ConvCfg<CIN, COUT, MODE, CW>::RPT, CONV_ROWS = ConvCfg<CIN, COUT, MODE, CW>::ROWS;
     __shared__ __align__(16) float s_w[WMAX];
     __shared__ float s_b[COUT];
     // head (MODE 2): W1 transposed [8][24] so that hidden-unit pairs are adjacent, then b1[24], w2[24], b2
@@ -133,7 +143,7 @@ __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
     const int cin = (MODE == 1) ? (a.cin_base + g * a.cin_step) : CIN;
     {
         const float *w = a.params + a.w_off[g];
-        const int n = 27 * cin * COUT;
+        const int n = CW ? 0 : 27 * cin * COUT;   // CW: the weights are already in the constant bank
         if (!a.flip) {
             for (int i = threadIdx.x; i < n; i += CONV_TPB) s_w[i] = w[i];
         } else {
@@ -185,7 +195,8 @@ __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             if (!((any >> j) & 1u)) continue;
-            const float *wk = s_w + (c + 9 * j) * cin * COUT;
+            const float *wk = s_w + (CW ? 0 : (c + 9 * j) * cin * COUT);
+            const int bk = CW ? a.bank_off[g] + (c + 9 * j) * cin * COUT : 0;
             // A row without this neighbour multiplies by zero instead of branching: acc + 0*w == acc bit for bit
             // (acc is never -0: it starts at +0 and x*w + acc rounds an exact zero to +0), so the result does not
             // depend on which rows share a thread -- encoder and decoder batches stay bit-identical.
@@ -209,12 +220,21 @@ __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
 #pragma unroll
             for (int ci = 0; ci < CIN; ++ci) {
                 if (MODE == 1 && ci >= cin) break;
-                const ulonglong2 *w2 = reinterpret_cast<const ulonglong2 *>(wk + ci * COUT);
                 u64 wq[HQ];
+                if constexpr (CW) {
+                    const ulonglong2 *w2 = reinterpret_cast<const ulonglong2 *>(&c_bank[bk + ci * COUT]);
 #pragma unroll
-                for (int q = 0; q < HQ; q += 2) {
-                    const ulonglong2 t = w2[q >> 1];
-                    wq[q] = t.x, wq[q + 1] = t.y;
+                    for (int q = 0; q < HQ; q += 2) {
+                        const ulonglong2 t = w2[q >> 1];
+                        wq[q] = t.x, wq[q + 1] = t.y;
+                    }
+                } else {
+                    const ulonglong2 *w2 = reinterpret_cast<const ulonglong2 *>(wk + ci * COUT);
+#pragma unroll
+                    for (int q = 0; q < HQ; q += 2) {
+                        const ulonglong2 t = w2[q >> 1];
+                        wq[q] = t.x, wq[q + 1] = t.y;
+                    }
                 }
 #pragma unroll
                 for (int r = 0; r < CONV_RPT; ++r) {
@@ -302,6 +322,37 @@ __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
 #pragma unroll
             for (int w = 0; w < CONV_TPB / 32; ++w) t += s_red[w];
             a.bits_partial[blockIdx.y * gridDim.x + blockIdx.x] = t;
+        }
+    }
+}
+
+
+// Stage the weights of a set of conv launches in the layout their kernels read (forward: as stored; grad-input:
+// W'[k][ci][co] = W_f[26-k][co][ci]) into a global buffer, fill after fill; net.cu copies a fill into the bank
+// right before the first launch that needs it.
+struct BankItem {
+    int w_off;   // parameter offset of the [27][..][..] kernel
+    int flip;    // grad-input layout
+    int cin, cout;  // dims of the CONSUMING launch (gathered channels, produced channels)
+    int fill, dst;  // fill index, float offset inside the fill
+};
+constexpr int BANK_MAX_ITEMS = 64;
+struct BankItems {
+    int n;
+    int fill_base[16];   // float offset of each fill inside the staging buffer
+    BankItem it[BANK_MAX_ITEMS];
+};
+__global__ void __launch_bounds__(256) bank_stage_kernel(const float *__restrict__ params, const BankItems items, float *__restrict__ stage) {
+    const BankItem it = items.it[blockIdx.x];
+    const float *w = params + it.w_off;
+    float *dst = stage + items.fill_base[it.fill] + it.dst;
+    const int n = 27 * it.cin * it.cout;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        if (!it.flip) {
+            dst[i] = w[i];
+        } else {
+            const int k = i / (it.cin * it.cout), r = i % (it.cin * it.cout), ci = r / it.cout, co = r % it.cout;
+            dst[i] = w[(26 - k) * it.cin * it.cout + co * it.cin + ci];
         }
     }
 }

@@ -298,6 +298,33 @@ def test_encode_decode_lossless_and_bpp(L, O):
         assert (orc.decode_u16(rows, got, n) == sym).all()
 
 
+def test_weight_bank_variant_is_bit_identical(L, O):
+    """The training forward reads the conv weights from the constant bank (uniform-register FFMA2 operands), the
+    coding forward from shared memory: same arithmetic, same order -> the same probability bits."""
+    g, S, sd, flat, fr = _net_case(L, O)
+    params = flat.cuda()
+    tr_run = L.net.NetRunner(S, fr.tables.n_rows, "cuda", train=True)
+    inf_run = L.net.NetRunner(S, fr.tables.n_rows, "cuda", train=False)
+    a = tr_run.forward(params, fr.tables, train=True, loss_scale=1.0 / fr.point_num, want_probs=True, want_cdf=True)
+    pa, ca, ba = a["probs"].clone(), a["cdf"].clone(), a["bits"].clone()
+    b = inf_run.forward(params, fr.tables, train=False, want_probs=True, want_cdf=True)
+    assert torch.equal(pa, b["probs"]) and torch.equal(ca, b["cdf"]) and torch.equal(ba, b["bits"])
+    # and on a side stream (which does not own the bank: shared-memory variant even with train=True)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        run2 = L.net.NetRunner(S, fr.tables.n_rows, "cuda", train=True)
+        c = run2.forward(params, fr.tables, train=True, loss_scale=1.0 / fr.point_num, want_probs=True)
+        grad2 = torch.empty_like(params)
+        run2.backward(params, fr.tables, grad2)
+        pc = c["probs"].clone()
+    side.synchronize()
+    grad1 = torch.empty_like(params)
+    tr_run.backward(params, fr.tables, grad1)
+    torch.cuda.synchronize()
+    assert torch.equal(pc, pa) and torch.equal(grad1, grad2)
+
+
 def test_batched_and_sequential_cdfs_identical(L, O):
     """Encoder (teacher-forced, all scales in one launch set) and decoder (per scale, stage by stage) must see
     bit-identical 16-bit CDFs: the precondition of lossless decoding."""
