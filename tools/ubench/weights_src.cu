@@ -298,6 +298,144 @@ void run_sp(const float *x, const float *w, float *y, int n, const char *name) {
     printf("%-28s %8.1f us  %6.2f TFLOP/s (%4.1f%% of 74.4)  err=%s\n", name, ms * 1e3, 2 * macs / ms / 1e9, 2 * macs / ms / 1e9 / 74.4 * 100, cudaGetErrorString(cudaGetLastError()));
 }
 
+// variant CP: constant-bank weights + register double-buffered gathers
+template <int RPT>
+__global__ void __launch_bounds__(128) kern_cp(const float *__restrict__ x, float *__restrict__ y, int n) {
+    const int g = blockIdx.y;
+    int row[RPT];
+    u64 acc[RPT][4];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        row[r] = blockIdx.x * 128 * RPT + r * 128 + threadIdx.x;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[r][q] = 0;
+    }
+    const float *xg = x + (size_t)g * n * 8;
+    auto load = [&](int k, float (&xv)[RPT][8]) {
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            int nb = row[r] + (k - 13) * 3;
+            nb = nb < 0 ? 0 : (nb >= n ? n - 1 : nb);
+            gather8(xg + (size_t)nb * 8, xv[r]);
+        }
+    };
+    auto fma = [&](int k, const float (&xv)[RPT][8]) {
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci) {
+            const ulonglong2 *w2 = reinterpret_cast<const ulonglong2 *>(&cw[g][k * 64 + ci * 8]);
+            const ulonglong2 t0 = w2[0], t1 = w2[1];
+            u64 wq[4] = {t0.x, t0.y, t1.x, t1.y};
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                const u64 xx = pack2(xv[r][ci], xv[r][ci]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) ffma2_acc(acc[r][q], xx, wq[q]);
+            }
+        }
+    };
+    float xa[RPT][8], xb[RPT][8];
+    load(0, xa);
+#pragma unroll 1
+    for (int k = 0; k < 26; k += 2) {
+        load(k + 1, xb);
+        fma(k, xa);
+        load(k + 2, xa);
+        fma(k + 1, xb);
+    }
+    fma(26, xa);
+#pragma unroll
+    for (int r = 0; r < RPT; ++r)
+        if (row[r] < n)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) reinterpret_cast<u64 *>(y + ((size_t)g * n + row[r]) * 8)[q] = acc[r][q];
+}
+template <int RPT>
+void run_cp(const float *x, float *y, int n, const char *name) {
+    dim3 grid((n + 128 * RPT - 1) / (128 * RPT), 8);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    for (int i = 0; i < 3; ++i) kern_cp<RPT><<<grid, 128>>>(x, y, n);
+    cudaEventRecord(e0);
+    const int it = 10;
+    for (int i = 0; i < it; ++i) kern_cp<RPT><<<grid, 128>>>(x, y, n);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms /= it;
+    double macs = (double)n * 8 * 27 * 64;
+    printf("%-28s %8.1f us  %6.2f TFLOP/s (%4.1f%% of 74.4)  err=%s\n", name, ms * 1e3, 2 * macs / ms / 1e9, 2 * macs / ms / 1e9 / 74.4 * 100, cudaGetErrorString(cudaGetLastError()));
+}
+
+// variant H: half of the weights (ci < SPLIT) from shared memory, the rest from the constant bank
+template <int RPT, int SPLIT>
+__global__ void __launch_bounds__(128) kern_h(const float *__restrict__ x, const float *__restrict__ wg, float *__restrict__ y, int n) {
+    __shared__ __align__(16) float s_w[27 * 64];
+    const int g = blockIdx.y;
+    for (int i = threadIdx.x; i < 27 * 64; i += 128) s_w[i] = wg[g * 27 * 64 + i];
+    __syncthreads();
+    int row[RPT];
+    u64 acc[RPT][4];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        row[r] = blockIdx.x * 128 * RPT + r * 128 + threadIdx.x;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[r][q] = 0;
+    }
+    const float *xg = x + (size_t)g * n * 8;
+#pragma unroll 1
+    for (int k = 0; k < 27; ++k) {
+        float xv[RPT][8];
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            int nb = row[r] + (k - 13) * 3;
+            nb = nb < 0 ? 0 : (nb >= n ? n - 1 : nb);
+            gather8(xg + (size_t)nb * 8, xv[r]);
+        }
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci) {
+            u64 wq[4];
+            if (ci < SPLIT) {
+                const ulonglong2 *w2 = reinterpret_cast<const ulonglong2 *>(s_w + k * 64 + ci * 8);
+                const ulonglong2 t0 = w2[0], t1 = w2[1];
+                wq[0] = t0.x, wq[1] = t0.y, wq[2] = t1.x, wq[3] = t1.y;
+            } else {
+                const ulonglong2 *w2 = reinterpret_cast<const ulonglong2 *>(&cw[g][k * 64 + ci * 8]);
+                const ulonglong2 t0 = w2[0], t1 = w2[1];
+                wq[0] = t0.x, wq[1] = t0.y, wq[2] = t1.x, wq[3] = t1.y;
+            }
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                const u64 xx = pack2(xv[r][ci], xv[r][ci]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) ffma2_acc(acc[r][q], xx, wq[q]);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RPT; ++r)
+        if (row[r] < n)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) reinterpret_cast<u64 *>(y + ((size_t)g * n + row[r]) * 8)[q] = acc[r][q];
+}
+template <int RPT, int SPLIT>
+void run_h(const float *x, const float *w, float *y, int n, const char *name) {
+    dim3 grid((n + 128 * RPT - 1) / (128 * RPT), 8);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    for (int i = 0; i < 3; ++i) kern_h<RPT, SPLIT><<<grid, 128>>>(x, w, y, n);
+    cudaEventRecord(e0);
+    const int it = 10;
+    for (int i = 0; i < it; ++i) kern_h<RPT, SPLIT><<<grid, 128>>>(x, w, y, n);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms /= it;
+    double macs = (double)n * 8 * 27 * 64;
+    printf("%-28s %8.1f us  %6.2f TFLOP/s (%4.1f%% of 74.4)  err=%s\n", name, ms * 1e3, 2 * macs / ms / 1e9, 2 * macs / ms / 1e9 / 74.4 * 100, cudaGetErrorString(cudaGetLastError()));
+}
+
 int main() {
     const int n = 277000;
     float *x, *y, *w;
@@ -322,6 +460,10 @@ int main() {
     run_s<4, 75>(x, w, y, n, "staged RPT=4 smem75K(3blk)");
     run_s<4, 110>(x, w, y, n, "staged RPT=4 smem110K(2blk)");
     run_s<2, 32>(x, w, y, n, "staged RPT=2 smem32K");
+    run_cp<2>(x, y, n, "const+prefetch RPT=2");
+    run_cp<4>(x, y, n, "const+prefetch RPT=4");
+    run_h<4, 2>(x, w, y, n, "hybrid 2 smem + 6 const RPT=4");
+    run_h<4, 4>(x, w, y, n, "hybrid 4 smem + 4 const RPT=4");
     run<1, 1>(x, w, y, n, "const RPT=1");
     run<2, 1>(x, w, y, n, "const RPT=2");
     run<4, 1>(x, w, y, n, "const RPT=4");
