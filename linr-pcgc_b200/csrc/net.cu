@@ -7,6 +7,7 @@
 #include <stdarg.h>
 
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "net_kernels.cuh"
@@ -257,6 +258,7 @@ struct BankOwner {
     bool owned = false;
     cudaStream_t stream = nullptr;
     int device = -1;
+    std::thread::id thread;   // fills and launches of two host threads would interleave even on one stream
 } g_bank_owner;
 
 bool bank_claim(cudaStream_t s) {
@@ -267,9 +269,10 @@ bool bank_claim(cudaStream_t s) {
     std::lock_guard<std::mutex> lock(g_bank_owner.mu);
     if (!g_bank_owner.owned) {
         g_bank_owner.owned = true, g_bank_owner.stream = s, g_bank_owner.device = dev;
+        g_bank_owner.thread = std::this_thread::get_id();
         return true;
     }
-    return g_bank_owner.stream == s && g_bank_owner.device == dev;
+    return g_bank_owner.stream == s && g_bank_owner.device == dev && g_bank_owner.thread == std::this_thread::get_id();
 }
 
 struct BankCtx {   // lives for one linr_net_forward(train) / linr_net_backward call on the owning stream
