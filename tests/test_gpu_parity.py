@@ -269,6 +269,46 @@ def test_single_layer_conv_entry_points(L, O):
             np.testing.assert_allclose(db.cpu().numpy(), dy.sum(0).numpy(), rtol=RTOL, atol=1e-4)
 
 
+def test_full_size_conv_identities(L):
+    """Size-independent properties of the three conv kernels on a loot-sized frame (all 7 scales, 277 k rows), no
+    oracle needed: (1) an all-ones input gives y[o] = sum over the PRESENT offsets of the column sums of W[k] -- an
+    independent formula on the kernel map's presence bits; (2) adjointness <conv(x), dy> = <x, conv^T(dy)> ties the
+    grad-input kernel to the forward one; (3) <conv(x), dy> = <W, dW> and db = sum(dy) tie the weight-gradient kernel to
+    it; (4) linearity."""
+    pts = L.synth.make_sequence("loot", 1, device="cuda")[0]
+    fr = L.frame.prepare_frame(pts, None, 64)
+    t = fr.tables
+    n = t.n_rows
+    assert n > 250_000
+    gen = torch.Generator(device="cuda").manual_seed(17)
+    bits = torch.stack([(t.mask.to(torch.int64) >> (3 * (k % 9) + k // 9)) & 1 for k in range(27)], dim=1).double()   # [n,27]
+    for cin, cout in ((8, 8), (8, 4), (4, 4)):
+        W = torch.randn(27, cin, cout, generator=gen, device="cuda") * 0.2
+        x = torch.randn(n, cin, generator=gen, device="cuda")
+        dy = torch.randn(n, cout, generator=gen, device="cuda")
+        # (1) ones
+        y1 = L.net.spconv27_fwd(torch.ones(n, cin, device="cuda"), W, None, t)
+        want = bits @ W.double().sum(dim=1)                                   # [n,27] @ [27,cout]
+        assert (y1.double() - want).abs().max().item() < 1e-4
+        # (2) adjoint of the forward conv
+        y = L.net.spconv27_fwd(x, W, None, t)
+        dx = L.net.spconv27_bwd_in(dy, W, t)
+        lhs = (y.double() * dy.double()).sum().item()
+        rhs = (x.double() * dx.double()).sum().item()
+        scale = (y.double().abs() * dy.double().abs()).sum().item()
+        assert abs(lhs - rhs) <= 1e-6 * scale, (cin, cout, lhs, rhs)
+        # (3) weight gradient
+        dW, db = L.net.spconv27_bwd_w(x, dy, t)
+        assert abs(lhs - (W.double() * dW.double()).sum().item()) <= 1e-6 * scale
+        ref_db = dy.double().sum(0)
+        assert (db.double() - ref_db).abs().max().item() <= 1e-5 * dy.double().abs().sum(0).max().item()
+        # (4) linearity in the input
+        x2 = torch.randn(n, cin, generator=gen, device="cuda")
+        ya = L.net.spconv27_fwd(2.0 * x - 0.5 * x2, W, None, t)
+        yb = 2.0 * y - 0.5 * L.net.spconv27_fwd(x2, W, None, t)
+        assert (ya - yb).abs().max().item() < 1e-4 * max(1.0, yb.abs().max().item())
+
+
 # ------------------------------------------------------------------------------------------------ coding
 def test_encode_decode_lossless_and_bpp(L, O):
     g, S, sd, flat, fr = _net_case(L, O)
