@@ -403,7 +403,8 @@ struct BwdWCfg {
     static constexpr int CI = (MODE == 1) ? 7 : CIN;                    // accumulated input width (bit inputs: up to 7)
     static constexpr int NK = (CIN == 4 && COUT == 4) ? 3 : 1;           // offsets per thread: the dz planes of its column
     static constexpr int SLOTS = 27 / NK + 1;                            // warps of work per (chunk, group); last = bias
-    static constexpr int WPB = (NK == 3) ? 5 : 7;                        // warps per block
+    // warps per block (measured: 7 for the 8->8 float conv -- dy sharing matters most; 4 for 8->4 and bit inputs)
+    static constexpr int WPB = (NK == 3) ? 5 : ((CIN == 8 && COUT == 8 && MODE == 0) ? 7 : 4);
     static constexpr int GX = (SLOTS + WPB - 1) / WPB;                   // blocks per (chunk, group)
     static constexpr int TPB = 32 * WPB;
     // register cap: 128 -> 4 warps per SM sub-partition (16 K registers each), 80 -> 6
