@@ -371,11 +371,13 @@ struct BlockBufs {  // activations of G blocks, group stride = R * C
 // the five inner layers of the GDFE block and of the seven LDFE blocks can share one 8-group launch.
 // in_bits: input are the low (cin_base + g*cin_step) occupancy bits; else float x [R,8].
 void block_A_forward(const float *params, const BlockL *L, int G, const RowMap &m, bool in_bits, const uint8_t *occ, int cin_base,
-                     int cin_step, Tens x, float *y, cudaStream_t s) {
+                     int cin_step, Tens x, float *y, float *t1, cudaStream_t s) {
     const int64_t R = m.n_rows;
-    ConvArgs a = conv_args(m, params);  // ConvA + ReLU -> y
+    ConvArgs a = conv_args(m, params);  // ConvA + ReLU -> y, and in its epilogue conv1_0 (k=1) + ReLU -> t1
     for (int g = 0; g < G; ++g) a.w_off[g] = L[g].A_w, a.b_off[g] = L[g].A_b;
     a.y = T(y, R * 8, 8), a.relu = 1;
+    a.pw_mode = 1, a.pw_relu = 1, a.y2 = T(t1, R * 4, 4);
+    for (int g = 0; g < G; ++g) a.pw_w_off[g] = L[g].c10_w, a.pw_b_off[g] = L[g].c10_b;
     if (in_bits) {
         a.occ = occ, a.cin_base = cin_base, a.cin_step = cin_step;
         launch_conv<8, 8, 1>(a, G, s);
@@ -387,12 +389,6 @@ void block_A_forward(const float *params, const BlockL *L, int G, const RowMap &
 
 void block_mid_forward(const float *params, const BlockL *L, int G, const RowMap &m, const BlockBufs &b, cudaStream_t s) {
     const int64_t R = m.n_rows;
-    {  // conv1_0 (k=1) + ReLU -> t1
-        PwArgs a = pw_args(R, params);
-        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].c10_w, a.b_off[g] = L[g].c10_b;
-        a.x = T(b.y, R * 8, 8), a.y = T(b.t1, R * 4, 4), a.relu = 1;
-        launch_pw<8, 4>(a, G, s);
-    }
     {  // conv0_0 + ReLU -> t0
         ConvArgs a = conv_args(m, params);
         for (int g = 0; g < G; ++g) a.w_off[g] = L[g].c00_w, a.b_off[g] = L[g].c00_b;
@@ -405,17 +401,13 @@ void block_mid_forward(const float *params, const BlockL *L, int G, const RowMap
         a.x = T(b.t0, R * 4, 4), a.y = T(b.z, R * 8, 8, 0), a.res = T(b.y, R * 8, 8, 0);
         launch_conv<4, 4, 0>(a, G, s);
     }
-    {  // conv1_1 + ReLU -> t2
+    {  // conv1_1 + ReLU -> t2, and in its epilogue conv1_2 (k=1) -> z[:, 4:8] = v + y[:, 4:8]
         ConvArgs a = conv_args(m, params);
         for (int g = 0; g < G; ++g) a.w_off[g] = L[g].c11_w, a.b_off[g] = L[g].c11_b;
         a.x = T(b.t1, R * 4, 4), a.y = T(b.t2, R * 4, 4), a.relu = 1;
+        a.pw_mode = 1, a.pw_relu = 0, a.y2 = T(b.z, R * 8, 8, 4), a.res2 = T(b.y, R * 8, 8, 4);
+        for (int g = 0; g < G; ++g) a.pw_w_off[g] = L[g].c12_w, a.pw_b_off[g] = L[g].c12_b;
         launch_conv<4, 4, 0>(a, G, s);
-    }
-    {  // conv1_2 (k=1) -> z[:, 4:8] = v + y[:, 4:8]
-        PwArgs a = pw_args(R, params);
-        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].c12_w, a.b_off[g] = L[g].c12_b;
-        a.x = T(b.t2, R * 4, 4), a.y = T(b.z, R * 8, 8, 4), a.res = T(b.y, R * 8, 8, 4);
-        launch_pw<4, 4>(a, G, s);
     }
 }
 
@@ -430,7 +422,7 @@ void block_B_forward(const float *params, const BlockL *L, int G, const RowMap &
 
 void block_forward(const float *params, const BlockL *L, int G, const RowMap &m, bool in_bits, const uint8_t *occ, int cin_base,
                    int cin_step, Tens x, const BlockBufs &b, Tens out, Tens res_out, cudaStream_t s) {
-    block_A_forward(params, L, G, m, in_bits, occ, cin_base, cin_step, x, b.y, s);
+    block_A_forward(params, L, G, m, in_bits, occ, cin_base, cin_step, x, b.y, b.t1, s);
     block_mid_forward(params, L, G, m, b, s);
     block_B_forward(params, L, G, m, b.z, out, res_out, s);
 }
@@ -664,8 +656,8 @@ int linr_net_forward(const float *d_params, int scale_num, const linr_rows *rows
     }
     // ConvA of the GDFE block (float input f0, group 7) and of the 7 LDFE blocks (occupancy bits, teacher forcing)
     BlockBufs all{w.ob_y, w.ob_t1, w.ob_t0, w.ob_t2, w.ob_z};
-    block_A_forward(d_params, &L.bin, 1, m, false, nullptr, 0, 0, T(w.f0, 0, 8), w.bi_y, s);
-    block_A_forward(d_params, L.ob, 7, m, true, rows->d_occ, 1, 1, TN(), w.ob_y, s);
+    block_A_forward(d_params, &L.bin, 1, m, false, nullptr, 0, 0, T(w.f0, 0, 8), w.bi_y, w.bi_t1, s);
+    block_A_forward(d_params, L.ob, 7, m, true, rows->d_occ, 1, 1, TN(), w.ob_y, w.ob_t1, s);
     // the five inner layers of all eight blocks in 8-group launches
     block_mid_forward(d_params, L.blk8, 8, m, all, s);
     // ConvB: g = block_in(f0) -> hh[0], then hh[k+1] = g + LDFE_k(occ[:, :k+1])

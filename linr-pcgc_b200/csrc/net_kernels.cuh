@@ -84,6 +84,13 @@ struct ConvArgs {
     float *bits_partial;  // [gridDim.y * gridDim.x] or null
     int64_t out_ld;       // row count used as the stage stride of probs/cdf/dz
     int bank_off[MAXG];   // CW variant: float offset of each group's staged weights in the constant bank
+    // fused kernel_size-1 conv of the Inception block (MODE 0/1 only), same arithmetic order as pw_kernel:
+    //  1: y2 = [relu](o @ Wp[COUT,4] + bp [+ res2])                 forward conv1_0 after ConvA, conv1_2 after conv1_1
+    //  2: y2 = [mask2 > 0](o[4:8] @ Wp[4,4]^T)                      backward of conv1_2 after ConvB^T
+    //  3: o += x2 @ Wp[8,4]^T  (before the ReLU mask of o)          backward of conv1_0 inside conv0_0^T
+    int pw_mode, pw_relu;
+    int pw_w_off[MAXG], pw_b_off[MAXG];
+    Tens y2, res2, x2, mask2;
 };
 
 constexpr int CONV_TPB = 128;
@@ -139,8 +146,25 @@ __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
     // head (MODE 2): W1 transposed [8][24] so that hidden-unit pairs are adjacent, then b1[24], w2[24], b2
     __shared__ __align__(16) float s_head[(MODE == 2) ? (24 * 8 + 24 + 24 + 4) : 4];
     __shared__ float s_red[CONV_TPB / 32];
+    __shared__ float s_pw[(MODE == 2) ? 1 : 36];   // fused pointwise weights [in][out] + bias
     const int g = blockIdx.y;
     const int cin = (MODE == 1) ? (a.cin_base + g * a.cin_step) : CIN;
+    if constexpr (MODE != 2) {
+        if (a.pw_mode && threadIdx.x < 36) {
+            const float *wp = a.params + a.pw_w_off[g];
+            const int i = threadIdx.x;
+            float v = 0.f;
+            if (a.pw_mode == 1) {          // s_pw[ci*4 + co] = W[ci][co], ci < COUT;  bias at 32..35
+                if (i < COUT * 4) v = wp[i];
+                else if (i >= 32) v = a.pw_b_off[g] >= 0 ? a.params[a.pw_b_off[g] + (i - 32)] : 0.f;
+            } else if (a.pw_mode == 2) {   // s_pw[ci*4 + co] = W[co][ci]  (ci: channel of o[4:8], co: channel of y2)
+                if (i < 16) v = wp[(i & 3) * 4 + (i >> 2)];
+            } else {                       // s_pw[co*8 + ci] = W[ci][co]  (co: channel of x2, ci: channel of o)
+                if (i < 32) v = wp[(i & 7) * 4 + (i >> 3)];
+            }
+            s_pw[i] = v;
+        }
+    }
     {
         const float *w = a.params + a.w_off[g];
         const int n = CW ? 0 : 27 * cin * COUT;   // CW: the weights are already in the constant bank
@@ -268,6 +292,20 @@ __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
 #pragma unroll
                 for (int co = 0; co < COUT; ++co) o[co] += t[co];
             }
+            if constexpr (COUT == 8) {
+                if (a.pw_mode == 3) {
+                    float xv2[4], t[8];
+                    load_row<4>(tptr(a.x2, g, row[r]), xv2);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) t[i] = 0.f;
+#pragma unroll
+                    for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+                        for (int co = 0; co < 8; ++co) t[co] = fmaf(xv2[ci], s_pw[ci * 8 + co], t[co]);
+#pragma unroll
+                    for (int co = 0; co < 8; ++co) o[co] = t[co] + o[co];
+                }
+            }
             if (a.relu) {
 #pragma unroll
                 for (int co = 0; co < COUT; ++co) o[co] = fmaxf(o[co], 0.f);
@@ -279,6 +317,40 @@ __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
                 for (int co = 0; co < COUT; ++co) o[co] = t[co] > 0.f ? o[co] : 0.f;
             }
             store_row<COUT>(tptr(a.y, g, row[r]), o);
+            if (a.pw_mode == 1) {
+                float t[4];
+#pragma unroll
+                for (int co = 0; co < 4; ++co) t[co] = 0.f;
+#pragma unroll
+                for (int ci = 0; ci < COUT; ++ci)
+#pragma unroll
+                    for (int co = 0; co < 4; ++co) t[co] = fmaf(o[ci], s_pw[ci * 4 + co], t[co]);
+#pragma unroll
+                for (int co = 0; co < 4; ++co) t[co] += s_pw[32 + co];
+                if (a.res2.p) {
+                    float u[4];
+                    load_row<4>(tptr(a.res2, g, row[r]), u);
+#pragma unroll
+                    for (int co = 0; co < 4; ++co) t[co] += u[co];
+                }
+                if (a.pw_relu) {
+#pragma unroll
+                    for (int co = 0; co < 4; ++co) t[co] = fmaxf(t[co], 0.f);
+                }
+                store_row<4>(tptr(a.y2, g, row[r]), t);
+            } else if (COUT == 8 && a.pw_mode == 2) {
+                float t[4], u[4];
+#pragma unroll
+                for (int co = 0; co < 4; ++co) t[co] = 0.f;
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+                    for (int co = 0; co < 4; ++co) t[co] = fmaf(o[(COUT == 8 ? 4 : 0) + ci], s_pw[ci * 4 + co], t[co]);
+                load_row<4>(tptr(a.mask2, g, row[r]), u);
+#pragma unroll
+                for (int co = 0; co < 4; ++co) t[co] = u[co] > 0.f ? t[co] : 0.f;
+                store_row<4>(tptr(a.y2, g, row[r]), t);
+            }
         } else {
             if (a.y.p) store_row<COUT>(tptr(a.y, g, row[r]), o);
             // MLP_k 8 -> 24 -> 1 (models/upsample.py:49-55,156-160); hidden units in pairs, inputs in order
