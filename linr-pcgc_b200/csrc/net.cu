@@ -471,15 +471,29 @@ void block_Bmid_backward(const float *params, const BlockL *L, int G, const RowM
     const Tens dz = T(gr.dz, R * 8, 8), dzl = T(gr.dz, R * 8, 8, 0), dzh = T(gr.dz, R * 8, 8, 4);
     const Tens dt0 = T(gr.dt0, R * 4, 4), dt1 = T(gr.dt1, R * 4, 4), dt2 = T(gr.dt2, R * 4, 4), dy = T(gr.dy, R * 8, 8);
 
-    // ConvB: dW, then dz = B^T dout
+    // ConvB: dW, then dz = B^T dout; its epilogue also applies conv1_2^T (k=1): dt2 = [t2 > 0](dz[:, 4:8] @ W12^T)
     offs(&BlockL::B_w, &BlockL::B_b);
     launch_bwd_w<8, 8, 0>(m, w, P, wo, bo, G, z, dout, nullptr, 0, 0, s);
     {
         ConvArgs a = conv_args(m, params);
-        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].B_w;
+        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].B_w, a.pw_w_off[g] = L[g].c12_w, a.pw_b_off[g] = -1;
         a.flip = 1, a.x = dout, a.y = dz;
+        a.pw_mode = 2, a.y2 = dt2, a.mask2 = t2;
         launch_conv<8, 8, 0>(a, G, s);
     }
+    // path 1 first (its dt1 is needed by the fused epilogue of conv0_0^T): conv1_2 (k=1) weights, conv1_1, conv1_0
+    offs(&BlockL::c12_w, &BlockL::c12_b);
+    launch_pw_bwd_w<4, 4>(R, w, P, wo, bo, G, t2, dzh, s);
+    offs(&BlockL::c11_w, &BlockL::c11_b);
+    launch_bwd_w<4, 4, 0>(m, w, P, wo, bo, G, t1, dt2, nullptr, 0, 0, s);
+    {
+        ConvArgs a = conv_args(m, params);
+        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].c11_w;
+        a.flip = 1, a.x = dt2, a.y = dt1, a.rmask = t1;
+        launch_conv<4, 4, 0>(a, G, s);
+    }
+    offs(&BlockL::c10_w, &BlockL::c10_b);
+    launch_pw_bwd_w<8, 4>(R, w, P, wo, bo, G, y, dt1, s);
     // path 0: conv0_1 then conv0_0
     offs(&BlockL::c01_w, &BlockL::c01_b);
     launch_bwd_w<4, 4, 0>(m, w, P, wo, bo, G, t0, dzl, nullptr, 0, 0, s);
@@ -491,36 +505,12 @@ void block_Bmid_backward(const float *params, const BlockL *L, int G, const RowM
     }
     offs(&BlockL::c00_w, &BlockL::c00_b);
     launch_bwd_w<8, 4, 0>(m, w, P, wo, bo, G, y, dt0, nullptr, 0, 0, s);
-    {  // dy = dz (residual) + c00^T dt0
+    {  // dy = [y > 0](dz (residual) + c00^T dt0 + dt1 @ W10^T): conv1_0^T (k=1) is applied in the epilogue
         ConvArgs a = conv_args(m, params);
-        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].c00_w;
-        a.flip = 1, a.x = dt0, a.y = dy, a.res = dz;
+        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].c00_w, a.pw_w_off[g] = L[g].c10_w, a.pw_b_off[g] = -1;
+        a.flip = 1, a.x = dt0, a.y = dy, a.res = dz, a.rmask = y;
+        a.pw_mode = 3, a.x2 = dt1;
         launch_conv<4, 8, 0>(a, G, s);
-    }
-    // path 1: conv1_2 (k=1), conv1_1, conv1_0 (k=1)
-    offs(&BlockL::c12_w, &BlockL::c12_b);
-    launch_pw_bwd_w<4, 4>(R, w, P, wo, bo, G, t2, dzh, s);
-    {
-        PwArgs a = pw_args(R, params);
-        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].c12_w;
-        a.transpose = 1, a.x = dzh, a.y = dt2, a.rmask = t2;
-        launch_pw<4, 4>(a, G, s);
-    }
-    offs(&BlockL::c11_w, &BlockL::c11_b);
-    launch_bwd_w<4, 4, 0>(m, w, P, wo, bo, G, t1, dt2, nullptr, 0, 0, s);
-    {
-        ConvArgs a = conv_args(m, params);
-        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].c11_w;
-        a.flip = 1, a.x = dt2, a.y = dt1, a.rmask = t1;
-        launch_conv<4, 4, 0>(a, G, s);
-    }
-    offs(&BlockL::c10_w, &BlockL::c10_b);
-    launch_pw_bwd_w<8, 4>(R, w, P, wo, bo, G, y, dt1, s);
-    {  // dy += c10^T dt1, then the ReLU mask of y
-        PwArgs a = pw_args(R, params);
-        for (int g = 0; g < G; ++g) a.w_off[g] = L[g].c10_w;
-        a.transpose = 1, a.x = dt1, a.y = dy, a.accum = 1, a.rmask = y;
-        launch_pw<4, 8>(a, G, s);
     }
 }
 
