@@ -337,14 +337,6 @@ void launch_conv(const ConvArgs &a, int G, cudaStream_t s) {
     ProfScope prof(cls, a.map.n_rows * G, s);
     conv27_kernel<CIN, COUT, MODE><<<grid, CONV_TPB, 0, s>>>(a);
 }
-template <int CIN, int COUT>
-void launch_pw(const PwArgs &a, int G, cudaStream_t s) {
-    if (a.n_rows <= 0) return;
-    dim3 grid((unsigned)ceil_div64(a.n_rows, PW_TPB), (unsigned)G);
-    ProfScope prof(K_PW, a.n_rows * G, s);
-    pw_kernel<CIN, COUT><<<grid, PW_TPB, 0, s>>>(a);
-}
-
 ConvArgs conv_args(const RowMap &m, const float *params) {
     ConvArgs a;
     memset(&a, 0, sizeof(a));
@@ -354,15 +346,6 @@ ConvArgs conv_args(const RowMap &m, const float *params) {
     a.out_ld = m.n_rows;
     return a;
 }
-PwArgs pw_args(int64_t n, const float *params) {
-    PwArgs a;
-    memset(&a, 0, sizeof(a));
-    a.n_rows = n;
-    a.params = params;
-    for (int g = 0; g < MAXG; ++g) a.b_off[g] = -1;
-    return a;
-}
-
 struct BlockBufs {  // activations of G blocks, group stride = R * C
     float *y, *t1, *t0, *t2, *z;
 };

@@ -640,68 +640,9 @@ __global__ void __launch_bounds__(BwdWCfg<CIN, COUT, MODE>::TPB) __maxnreg__((Bw
 }
 
 // ------------------------------------------------------------------------------------------------
-// Pointwise (kernel_size = 1) convs of the Inception block: y = x @ W[CIN,COUT] + b.
+// Pointwise (kernel_size = 1) convs of the Inception block.  Forward and grad-input run in the epilogues of the
+// 27-offset convs (pw_mode of conv27_kernel); only the weight gradients are separate launches.
 // ------------------------------------------------------------------------------------------------
-struct PwArgs {
-    int64_t n_rows;
-    const float *params;
-    int w_off[MAXG], b_off[MAXG];
-    int transpose;  // backward: dx[ci] = sum_co dy[co] * W[ci][co]  (template dims are (in,out) of THIS launch)
-    Tens x, y, res, rmask;
-    int relu, accum;
-};
-constexpr int PW_TPB = 256;
-
-template <int CIN, int COUT>
-__global__ void __launch_bounds__(PW_TPB) pw_kernel(const PwArgs a) {
-    __shared__ float s_w[CIN * COUT];
-    __shared__ float s_b[COUT];
-    const int g = blockIdx.y;
-    if (threadIdx.x < CIN * COUT) {
-        const int i = threadIdx.x, ci = i / COUT, co = i % COUT;
-        // forward: W[ci][co] row-major [CIN][COUT]; transpose: stored W_f[COUT][CIN], want s_w[ci][co] = W_f[co][ci]
-        s_w[i] = a.transpose ? a.params[a.w_off[g] + co * CIN + ci] : a.params[a.w_off[g] + i];
-    }
-    if (threadIdx.x < COUT) s_b[threadIdx.x] = a.b_off[g] >= 0 ? a.params[a.b_off[g] + threadIdx.x] : 0.f;
-    __syncthreads();
-    const int64_t row = blockIdx.x * (int64_t)PW_TPB + threadIdx.x;
-    if (row >= a.n_rows) return;
-    float xv[CIN], acc[COUT];
-    load_row<CIN>(tptr(a.x, g, row), xv);
-#pragma unroll
-    for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
-#pragma unroll
-    for (int ci = 0; ci < CIN; ++ci) {
-#pragma unroll
-        for (int co = 0; co < COUT; ++co) acc[co] = fmaf(xv[ci], s_w[ci * COUT + co], acc[co]);
-    }
-#pragma unroll
-    for (int co = 0; co < COUT; ++co) acc[co] += s_b[co];
-    if (a.res.p) {
-        float r[COUT];
-        load_row<COUT>(tptr(a.res, g, row), r);
-#pragma unroll
-        for (int co = 0; co < COUT; ++co) acc[co] += r[co];
-    }
-    if (a.accum) {
-        float r[COUT];
-        load_row<COUT>(tptr(a.y, g, row), r);
-#pragma unroll
-        for (int co = 0; co < COUT; ++co) acc[co] += r[co];
-    }
-    if (a.relu) {
-#pragma unroll
-        for (int co = 0; co < COUT; ++co) acc[co] = fmaxf(acc[co], 0.f);
-    }
-    if (a.rmask.p) {
-        float r[COUT];
-        load_row<COUT>(tptr(a.rmask, g, row), r);
-#pragma unroll
-        for (int co = 0; co < COUT; ++co) acc[co] = r[co] > 0.f ? acc[co] : 0.f;
-    }
-    store_row<COUT>(tptr(a.y, g, row), acc);
-}
-
 // dW[ci][co] = sum_r x[r][ci] dy[r][co], db[co] = sum_r dy[r][co]; one partial per row chunk.
 struct PwBwdWArgs {
     int64_t n_rows;

@@ -18,7 +18,7 @@ enum KClass {
     K_BWDW84,
     K_BWDW44,
     K_BWDWBITS,     // conv27_bwd_w_kernel<8,8,1>
-    K_PW,           // pointwise (kernel_size 1) forward / grad-input
+    K_PW,           // (unused since the pointwise convs run in conv epilogues; kept so class ids stay stable)
     K_PWBWDW,       // pointwise weight gradient
     K_HEADBWD,      // head_bwd_rows + head_bwd_w
     K_SCE,          // sce_fwd / sce_bwd / sce_finalize
