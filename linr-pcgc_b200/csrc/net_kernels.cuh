@@ -811,7 +811,7 @@ __global__ void __launch_bounds__(SCE_BWD_TPB) sce_bwd_kernel(const SceArgs a, f
 #pragma unroll
                 for (int c = 0; c < 8; ++c) w2c[jj][c] = p[128 + c * 16 + j];
             }
-#pragma unroll 2
+#pragma unroll 4
             for (int64_t r = r0 + lane; r < r1; r += 32) {
                 const int rs = a.scale_fixed >= 0 ? a.scale_fixed : a.scale[r];
                 if (rs != s) continue;
