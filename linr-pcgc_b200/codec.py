@@ -110,7 +110,7 @@ def encode_frames(runner: NetRunner, params: torch.Tensor, frames: Sequence[Fram
                 cdfs.append(cdf[k, a:b])
                 syms.append(occ[a:b])
                 shifts.append(k)
-        streams = rc.encode_binary_batch(cdfs, syms, shifts, threads or max(4, (os.cpu_count() or 8) // max(1, coders)))
+        streams = rc.encode_binary_batch(cdfs, syms, shifts, threads or max(2, rc.host_cores() // max(1, coders)))
         return [pack_bitstream(streams[8 * s: 8 * s + 8]) for s in range(f.n_scales)]
 
     with ThreadPoolExecutor(max_workers=max(1, coders)) as pool:

@@ -82,7 +82,7 @@ def decode_gop(enc: EncodedGop, device="cuda", workers: Optional[int] = None) ->
     flat = model_compression.decompress_model(d, n, device)
     lows, mins = codec.unpack_low_xyz(enc.low_enc_bytes)
     jobs = [(fb, torch.from_numpy(lows[i]).to(device)) for i, fb in enumerate(enc.frame_bytes)]
-    dec = codec.decode_frames(flat, enc.scale_num, jobs, workers=workers or min(16, os.cpu_count() or 8))
+    dec = codec.decode_frames(flat, enc.scale_num, jobs, workers=workers or min(16, codec.rc.host_cores()))
     return [xyz + torch.from_numpy(mins[i].copy()).to(device) for i, xyz in enumerate(dec)]
 
 

@@ -15,6 +15,17 @@ import numpy as np
 from . import _lib
 
 
+def host_cores() -> int:
+    """Host cores this process may plan with: the box's cores divided by the ranks torchrun started on it (one rank
+    per GPU share the host; LOCAL_WORLD_SIZE is absent in single-process runs)."""
+    n = os.cpu_count() or 8
+    try:
+        n //= max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    except ValueError:
+        pass
+    return max(2, n)
+
+
 def _p(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 
@@ -61,7 +72,7 @@ def encode_binary_batch(cdf_mids: Sequence[np.ndarray], syms: Sequence[np.ndarra
     k = len(cdf_mids)
     if k == 0:
         return []
-    threads = threads or min(os.cpu_count() or 1, 32)
+    threads = threads or min(host_cores(), 32)
     cdf_mids = [np.ascontiguousarray(c).view(np.uint16) for c in cdf_mids]
     syms = [np.ascontiguousarray(s, dtype=np.uint8) for s in syms]
     ns = np.array([len(s) for s in syms], dtype=np.int64)
