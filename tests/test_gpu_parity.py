@@ -365,6 +365,33 @@ def test_weight_bank_variant_is_bit_identical(L, O):
     assert torch.equal(pc, pa) and torch.equal(grad1, grad2)
 
 
+def test_two_trainers_in_two_host_threads_match_serial_runs(L, O):
+    """The constant weight bank is owned by one (host thread, stream) pair; a second trainer running concurrently in
+    another host thread -- even on the same stream -- must fall back to the shared-memory kernels and still produce
+    exactly the parameters of a serial run."""
+    import threading
+    pts = L.synth.make_sequence("tiny", 2)
+    frames = [L.frame.prepare_frame(p.cuda(), None, 64) for p in pts]
+    S = frames[0].n_scales
+
+    def train(seed, out, key):
+        torch.cuda.set_device(0)
+        tr = L.trainer.GopTrainer(S, "cuda", seed=seed, max_rows=max(f.tables.n_rows for f in frames))
+        tr.fit(frames, 3)
+        torch.cuda.synchronize()
+        out[key] = tr.state.params.clone()
+
+    serial, conc = {}, {}
+    train(1, serial, "a")
+    train(2, serial, "b")
+    ths = [threading.Thread(target=train, args=(1, conc, "a")), threading.Thread(target=train, args=(2, conc, "b"))]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert torch.equal(serial["a"], conc["a"]) and torch.equal(serial["b"], conc["b"])
+
+
 def test_batched_and_sequential_cdfs_identical(L, O):
     """Encoder (teacher-forced, all scales in one launch set) and decoder (per scale, stage by stage) must see
     bit-identical 16-bit CDFs: the precondition of lossless decoding."""
