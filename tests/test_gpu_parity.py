@@ -132,6 +132,46 @@ def test_empty_and_single_point(L):
         L.frame.prepare_frame(torch.zeros((4, 3), dtype=torch.int32), None, 64)  # host tensor: no CPU path
 
 
+def test_c_abi_error_codes_and_messages(L, O):
+    """Error behaviour of the C ABI (include/linr_b200.h): negative return code + linr_last_error(), nothing launched.
+    The reference signals the same situations with Python asserts / exceptions."""
+    import ctypes as C
+    lib = L.lib.load()
+    g, S, sd, flat, fr = _net_case(L, O)
+    params = flat.cuda()
+    run = L.net.NetRunner(S, fr.tables.n_rows, "cuda", train=True)
+    rows = fr.tables.rows()
+    stream = L.lib.stream_ptr()
+    ptr = L.lib.ptr
+    # workspace too small
+    rc = lib.linr_net_forward(ptr(params), S, C.byref(rows), 1, 1.0, None, None, ptr(run.bits), ptr(run.ws), 1024, stream)
+    assert rc < 0 and b"workspace too small" in lib.linr_last_error()
+    rc = lib.linr_net_backward(ptr(params), S, C.byref(rows), ptr(torch.empty_like(params)), ptr(run.ws), 1024, stream)
+    assert rc < 0 and b"workspace too small" in lib.linr_last_error()
+    # scale_num out of range, stage out of range, bad bit depth, Adam step 0
+    assert lib.linr_net_forward(ptr(params), 0, C.byref(rows), 0, 0.0, None, None, None, ptr(run.ws), run.ws.numel(), stream) < 0
+    assert b"scale_num" in lib.linr_last_error()
+    assert lib.linr_net_decode_stage(ptr(params), S, C.byref(rows), 8, None, ptr(run.cdf), ptr(run.ws), run.ws.numel(), stream) < 0
+    assert b"stage" in lib.linr_last_error()
+    q = torch.empty(params.numel(), dtype=torch.uint8, device="cuda")
+    st = torch.empty(4, device="cuda")
+    assert lib.linr_param_quant(ptr(params), params.numel(), 9, ptr(q), ptr(torch.empty_like(params)), ptr(st), stream) < 0
+    assert b"bitdepth" in lib.linr_last_error()
+    z = torch.zeros_like(params)
+    assert lib.linr_adam_fused(ptr(params.clone()), ptr(z), ptr(z.clone()), ptr(z.clone()), params.numel(), 0, 0.01, 0.9, 0.999, 1e-8, 1e-4, stream) < 0
+    # unsupported channel counts of the single-layer entry points
+    x = torch.zeros(fr.tables.n_rows, 8, device="cuda")
+    assert lib.linr_spconv27_fwd(ptr(x), 6, ptr(torch.zeros(27 * 6 * 8, device="cuda")), None, ptr(x.clone()), 8, C.byref(rows), 0, stream) < 0
+    assert b"channels" in lib.linr_last_error()
+    # the Python wrappers turn every failure into LinrError and refuse host tensors
+    with pytest.raises(L.lib.LinrError):
+        L.net.spconv27_fwd(x.cpu(), torch.zeros(27, 8, 8), None, fr.tables)
+    torch.cuda.synchronize()
+    # nothing above left the device in an error state: a normal call still works
+    out = run.forward(params, fr.tables, train=True, loss_scale=1.0 / fr.point_num)
+    assert float(out["bits"].item()) > 0
+
+
 @pytest.mark.parametrize("shape,bits", [("loot", 10), ("owlii", 11)])
 def test_full_size_octree_round_trip(L, shape, bits):
     """BASELINE.json full sizes: size-independent properties (round trip, sortedness, idempotence)."""
