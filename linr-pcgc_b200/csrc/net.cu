@@ -201,7 +201,7 @@ struct NetWs {
     // backward
     float *dc, *dhh, *dg, *g_dz, *g_dt0, *g_dy, *g_dt2, *g_dt1, *df0;
     float *partial, *sce_rec;
-    float *stage;  // weight-bank staging (train only)
+    float *stage = nullptr;  // weight-bank staging (train only)
     bool ok = false;
     size_t used = 0;
 };
