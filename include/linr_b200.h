@@ -123,7 +123,23 @@ typedef struct {
     const uint8_t *d_nbr7;   /* [n_rows] */
     const uint8_t *d_scale;  /* [n_rows] scale index of each row, non-decreasing (scales are concatenated in order) */
     const uint8_t *d_occ;    /* [n_rows] 8-bit child occupancy (teacher forcing / decoded so far) */
+    const int32_t *d_tile_rng; /* [ceil(n_rows/128),6] from linr_tile_ranges, or NULL: per 128-row tile and dx = -1,0,+1 the
+                                * row range [lo,hi) of its neighbours.  With it the conv / weight-gradient kernels stage their
+                                * inputs in shared memory with bulk (TMA) copies; without it they gather through L1.  Same
+                                * results bit for bit either way.  When set, d_mask must be readable up to `ld` entries. */
+    const int32_t *d_pair_cnt;   /* [ceil(n_rows/256),32] and */
+    const uint32_t *d_pair_list; /* [ceil(n_rows/256),27,256] from linr_pair_lists, or NULL: per 256-row tile and kernel offset
+                                  * the existing (row, neighbour) pairs.  With them the kernels only touch occupied offsets. */
 } linr_rows;
+
+/* Neighbour row ranges per 128-row tile (see linr_rows.d_tile_rng); d_rng int32 [ceil(n_rows/128), 6] =
+ * (lo,hi) for dx = -1, 0, +1.  No reference counterpart (ME keeps per-offset in/out index lists instead). */
+int linr_tile_ranges(const linr_rows *rows, int32_t *d_rng, void *stream);
+
+/* Pair lists of the kernel map (see linr_rows.d_pair_cnt / d_pair_list): list (t,k) holds the rows of 256-row tile t that
+ * have a neighbour at offset k, in row order, as (row - 256 t) << 24 | neighbour_row; d_cnt[t*32 + k] of its 256 slots are
+ * valid.  Same information as ME's per-offset in/out kernel maps, tiled.  n_rows < 2^24. */
+int linr_pair_lists(const linr_rows *rows, int32_t *d_cnt, uint32_t *d_list, void *stream);
 
 /* Workspace sizes (bytes) for n_rows rows. `train`!=0 includes saved activations and gradients. */
 size_t linr_net_ws_bytes(int64_t n_rows, int train);

@@ -19,7 +19,8 @@ class LinrError(RuntimeError):
 class Rows(C.Structure):
     """struct linr_rows (include/linr_b200.h)."""
     _fields_ = [("n_rows", C.c_int64), ("ld", C.c_int64), ("d_anchor", C.c_void_p), ("d_mask", C.c_void_p),
-                ("d_nbr7", C.c_void_p), ("d_scale", C.c_void_p), ("d_occ", C.c_void_p)]
+                ("d_nbr7", C.c_void_p), ("d_scale", C.c_void_p), ("d_occ", C.c_void_p), ("d_tile_rng", C.c_void_p),
+                ("d_pair_cnt", C.c_void_p), ("d_pair_list", C.c_void_p)]
 
 
 _P, _I64, _I, _F, _SZ = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
@@ -44,6 +45,8 @@ SIGNATURES = {
     "linr_hash_bytes": (_SZ, [_I64]),
     "linr_hash_build": (_I, [_P, _P, _I64, _P, _I64, _P]),
     "linr_nbr_build": (_I, [_P, _P, _I64, _P, _I64, _P, _P, _I64, _P, _P, _P]),
+    "linr_tile_ranges": (_I, [_RP, _P, _P]),
+    "linr_pair_lists": (_I, [_RP, _P, _P, _P]),
     "linr_hash_lookup": (_I, [_P, _P, _I64, _P, _I64, _P, _P]),
     "linr_param_count": (_I64, [_I]),
     "linr_param_offsets": (_I, [_I, C.POINTER(_I64), _I]),

@@ -206,6 +206,87 @@ __global__ void nbr_kernel(const int32_t *__restrict__ xyz, const uint8_t *__res
     }
 }
 
+
+// Per 128-row tile and per dx in {-1,0,+1}: the row range [lo, hi) that holds every neighbour of the tile's rows
+// with that dx.  Rows are x-major sorted, so o -> row(C[o] + delta) is monotone for a fixed delta: the neighbours of
+// a tile of consecutive rows sit in three nearly contiguous row ranges, which the conv / weight-gradient kernels
+// stage into shared memory with bulk (TMA) copies instead of gathering them line by line through L1.
+__global__ void __launch_bounds__(128) tile_range_kernel(const int32_t *__restrict__ anchor, int64_t ld,
+                                                         const uint32_t *__restrict__ mask, int64_t n, int32_t *__restrict__ rng) {
+    __shared__ int s_lo[4][3], s_hi[4][3];
+    const int64_t row = blockIdx.x * 128ll + threadIdx.x;
+    int lo[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, hi[3] = {0, 0, 0};
+    if (row < n) {
+        const uint32_t m = mask[row];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+            const uint32_t m3 = (m >> (3 * c)) & 7u;
+            if (m3) {
+                const int a = anchor[c * ld + row];
+                lo[c % 3] = min(lo[c % 3], a);
+                hi[c % 3] = max(hi[c % 3], a + __popc(m3));
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            lo[d] = min(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+            hi[d] = max(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) s_lo[threadIdx.x >> 5][d] = lo[d], s_hi[threadIdx.x >> 5][d] = hi[d];
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int d = threadIdx.x;
+        int l = s_lo[0][d], h = s_hi[0][d];
+        for (int w = 1; w < 4; ++w) l = min(l, s_lo[w][d]), h = max(h, s_hi[w][d]);
+        if (h <= l) l = 0, h = 0;
+        rng[blockIdx.x * 6 + 2 * d] = l;
+        rng[blockIdx.x * 6 + 2 * d + 1] = h;
+    }
+}
+
+// Pair lists: for every 256-row tile and every kernel offset k the (output row, neighbour row) pairs that exist, in
+// row order: entry = (row - tile_base) << 24 | neighbour_row.  One warp per (tile, column c) fills the three lists of
+// its column (k = c + 9 j) by ballot compaction, so a list is a deterministic function of the kernel map.  Lists have
+// a fixed capacity of 256 entries (list t,k starts at (t * 27 + k) * 256); cnt[t * 32 + k] entries are valid.
+// The conv and weight-gradient kernels walk these lists 32 pairs at a time: no lane ever multiplies by the zero of
+// an absent neighbour (14.3 of 27 offsets are occupied on a surface).
+__global__ void __launch_bounds__(288) pair_list_kernel(const int32_t *__restrict__ anchor, int64_t ld, const uint32_t *__restrict__ mask,
+                                                        int64_t n, int32_t *__restrict__ cnt, uint32_t *__restrict__ list) {
+    const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;   // 9 warps: one per (dx,dy) column
+    const int64_t tile = blockIdx.x, base = tile * 256;
+    int count[3] = {0, 0, 0};
+    for (int st = 0; st < 8; ++st) {
+        const int rl = st * 32 + lane;
+        const int64_t row = base + rl;
+        uint32_t m3 = 0;
+        int an = 0;
+        if (row < n) {
+            m3 = (mask[row] >> (3 * c)) & 7u;
+            if (m3) an = anchor[c * ld + row];
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const bool has = (m3 >> j) & 1u;
+            const uint32_t bal = __ballot_sync(0xffffffffu, has);
+            if (has) {
+                const int nb = an + __popc(m3 & ((1u << j) - 1u));
+                const int pos = count[j] + __popc(bal & ((1u << lane) - 1u));
+                list[(tile * 27 + (c + 9 * j)) * 256 + pos] = ((uint32_t)rl << 24) | (uint32_t)nb;
+            }
+            count[j] += __popc(bal);
+        }
+    }
+    if (lane < 3) cnt[tile * 32 + c + 9 * lane] = lane == 0 ? count[0] : (lane == 1 ? count[1] : count[2]);
+    if (c == 0 && lane >= 27) cnt[tile * 32 + lane] = 0;
+}
+
 struct SortWs {
     uint64_t *a, *b;
     int64_t *cnt;
@@ -392,6 +473,33 @@ int linr_nbr_build(const int32_t *d_xyz, const uint8_t *d_scale, int64_t n, cons
         ProfScope prof(K_COORD, 1, s);
         nbr_kernel<<<(int)ceil_div64(n, 128), 128, 0, s>>>(d_xyz, d_scale, n, (const HashSlot *)d_table, cap, d_nbr27, d_anchor,
                                                             ld, d_mask, d_nbr7);
+    }
+    LINR_LAUNCH_CHECK();
+    return LINR_OK;
+}
+
+int linr_tile_ranges(const linr_rows *rows, int32_t *d_rng, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    LINR_REQUIRE(rows && d_rng, "linr_tile_ranges: null argument");
+    LINR_REQUIRE(rows->ld >= rows->n_rows, "anchor leading dimension smaller than n_rows");
+    if (rows->n_rows <= 0) return LINR_OK;
+    {
+        ProfScope prof(K_COORD, 1, s);
+        tile_range_kernel<<<(int)ceil_div64(rows->n_rows, 128), 128, 0, s>>>(rows->d_anchor, rows->ld, rows->d_mask, rows->n_rows, d_rng);
+    }
+    LINR_LAUNCH_CHECK();
+    return LINR_OK;
+}
+
+int linr_pair_lists(const linr_rows *rows, int32_t *d_cnt, uint32_t *d_list, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    LINR_REQUIRE(rows && d_cnt && d_list, "linr_pair_lists: null argument");
+    LINR_REQUIRE(rows->ld >= rows->n_rows, "anchor leading dimension smaller than n_rows");
+    LINR_REQUIRE(rows->n_rows < (1ll << 24), "linr_pair_lists: entries hold 24-bit row indices (n_rows < 16,777,216)");
+    if (rows->n_rows <= 0) return LINR_OK;
+    {
+        ProfScope prof(K_COORD, 1, s);
+        pair_list_kernel<<<(int)ceil_div64(rows->n_rows, 256), 288, 0, s>>>(rows->d_anchor, rows->ld, rows->d_mask, rows->n_rows, d_cnt, d_list);
     }
     LINR_LAUNCH_CHECK();
     return LINR_OK;

@@ -214,11 +214,17 @@ int chunks_for(int64_t R) {
     return (int)nb;
 }
 
+// Row chunks of the weight-gradient partial sums: at most one per SM, whole 256-row tiles each
+void set_chunks(NetWs &w, int64_t R) {
+    const int cap = chunks_for(R);
+    w.chunk = (ceil_div64(R > 0 ? R : 1, cap) + BW_T - 1) / BW_T * BW_T;
+    w.n_chunks = (int)ceil_div64(R > 0 ? R : 1, w.chunk);
+}
+
 NetWs carve_net(void *ws, size_t bytes, int64_t R, int train, int P, int S) {
     NetWs w;
     w.R = R;
-    w.n_chunks = chunks_for(R);
-    w.chunk = (ceil_div64(R > 0 ? R : 1, w.n_chunks) + BW_T - 1) / BW_T * BW_T;  // whole tiles per chunk
+    set_chunks(w, R);
     WsCursor c(ws, bytes);
     const size_t r = (size_t)(R > 0 ? R : 1);
     w.f0 = c.take<float>(r * 8);
@@ -250,7 +256,17 @@ NetWs carve_net(void *ws, size_t bytes, int64_t R, int train, int P, int S) {
 inline Tens T(float *p, int64_t gs, int ld, int off = 0) { return Tens{p, gs, ld, off}; }
 inline Tens TN() { return Tens{nullptr, 0, 0, 0}; }
 
-RowMap map_of(const linr_rows *r) { return RowMap{r->d_anchor, r->ld, r->d_mask, r->n_rows}; }
+// LINR_NO_STAGING=1: every kernel gathers through L1 as if no tile ranges were given (A/B runs, parity tests)
+bool staging_enabled() {
+    static const bool off = getenv("LINR_NO_STAGING") != nullptr;
+    return !off;
+}
+
+RowMap map_of(const linr_rows *r) {
+    const bool st = staging_enabled();
+    return RowMap{r->d_anchor, r->ld, r->d_mask, r->n_rows, st ? r->d_tile_rng : nullptr, st ? r->d_pair_cnt : nullptr,
+                  st ? r->d_pair_list : nullptr};
+}
 
 // ---- weight bank (constant memory is one per process: a single stream owns it, everybody else uses shared memory)
 struct BankOwner {
@@ -302,9 +318,25 @@ struct BankScope {
     ~BankScope() { t_bank = nullptr; }
 };
 
+// dynamic shared memory above 48 KB has to be opted into once per function and device (`done`: the caller's flags
+// for THIS kernel instantiation)
+bool opt_in_smem(const void *kernel, int bytes, bool (&done)[64]) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+    if (!done[dev]) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        done[dev] = true;
+    }
+    return true;
+}
+
+// returns gridDim.x of the launch (the head kernel writes one bit-count partial per block)
 template <int CIN, int COUT, int MODE>
-void launch_conv(const ConvArgs &a, int G, cudaStream_t s) {
-    if (a.map.n_rows <= 0) return;
+int launch_conv(const ConvArgs &a, int G, cudaStream_t s) {
+    if (a.map.n_rows <= 0) return 0;
     constexpr int cls = MODE == 2 ? K_CONVHEAD : MODE == 1 ? K_CONVBITS : (CIN == 8 ? (COUT == 8 ? K_CONV88 : K_CONV84) : (COUT == 8 ? K_CONV48 : K_CONV44));
     if (MODE != 1 && t_bank && !a.bias_direct) {
         // every group's weights must sit in ONE fill of the plan; otherwise this launch stays on shared memory
@@ -330,12 +362,13 @@ void launch_conv(const ConvArgs &a, int G, cudaStream_t s) {
             dim3 grid((unsigned)ceil_div64(a.map.n_rows, (ConvCfg<CIN, COUT, MODE, true>::ROWS)), (unsigned)G);
             ProfScope prof(cls, a.map.n_rows * G, s);
             conv27_kernel<CIN, COUT, MODE, true><<<grid, CONV_TPB, 0, s>>>(b);
-            return;
+            return (int)grid.x;
         }
     }
     dim3 grid((unsigned)ceil_div64(a.map.n_rows, (ConvCfg<CIN, COUT, MODE>::ROWS)), (unsigned)G);
     ProfScope prof(cls, a.map.n_rows * G, s);
     conv27_kernel<CIN, COUT, MODE><<<grid, CONV_TPB, 0, s>>>(a);
+    return (int)grid.x;
 }
 ConvArgs conv_args(const RowMap &m, const float *params) {
     ConvArgs a;
@@ -423,10 +456,31 @@ void launch_bwd_w(const RowMap &m, const NetWs &w, int P, const int *w_off, cons
     for (int g = 0; g < G; ++g) a.w_off[g] = w_off[g], a.b_off[g] = b_off[g];
     a.x = x, a.dy = dy, a.occ = occ, a.cin_base = cin_base, a.cin_step = cin_step;
     a.partial = w.partial, a.P = P, a.chunk = w.chunk;
-    using Cfg = BwdWCfg<CIN, COUT, MODE>;
-    dim3 grid((unsigned)Cfg::GX, (unsigned)w.n_chunks, (unsigned)G);  // offset slots fastest: blocks sharing a row chunk run together
+    static const int no_x = getenv("LINR_BW3_NOX") ? atoi(getenv("LINR_BW3_NOX")) : 0;
+    a.no_xstage = no_x;
     constexpr int cls = MODE == 1 ? K_BWDWBITS : (COUT == 8 ? K_BWDW88 : (CIN == 8 ? K_BWDW84 : K_BWDW44));
     ProfScope prof(cls, m.n_rows * G, s);
+    // v3 (staged + pair lists) needs the tile ranges, the pair lists and plain, 16-byte aligned row arrays
+    const bool plain = m.tile_rng && m.pair_cnt && m.pair_list && (dy.off & 3) == 0 && (dy.gs & 3) == 0 &&
+                       (reinterpret_cast<uintptr_t>(dy.p) & 15) == 0 && (w.chunk % BW3_T) == 0 &&
+                       (MODE == 1 || (x.ld == CIN && (x.off & 3) == 0 && (x.gs & 3) == 0 && (reinterpret_cast<uintptr_t>(x.p) & 15) == 0));
+    auto launch3 = [&, G](auto kernel, int smem, bool (&ok)[64]) {
+        if (!opt_in_smem(reinterpret_cast<const void *>(kernel), smem, ok)) return false;
+        dim3 grid(2u, (unsigned)w.n_chunks, 1u);
+        a.groups = G;
+        kernel<<<grid, 32 * (BW3_NW + 1), smem, s>>>(a);
+        return true;
+    };
+    // measured (round 2, profiles/README.md): v3 wins for the 8->8 float conv (64 accumulators per lane, FMA-heavy pairs);
+    // the 4-channel and bit-input gradients do too little arithmetic per pair and stay on the lane = row kernel
+    if constexpr (CIN == 8 && COUT == 8 && MODE == 0) {
+        if (plain && dy.ld == COUT) {
+            static bool ok[64] = {false};
+            if (launch3(conv27_bwd_w3_kernel<CIN, COUT, MODE, COUT>, BwdW3Cfg<CIN, COUT, MODE, COUT>::SMEM, ok)) return;
+        }
+    }
+    using Cfg = BwdWCfg<CIN, COUT, MODE>;
+    dim3 grid((unsigned)Cfg::GX, (unsigned)w.n_chunks, (unsigned)G);  // offset slots fastest: blocks sharing a row chunk run together
     conv27_bwd_w_kernel<CIN, COUT, MODE><<<grid, Cfg::TPB, 0, s>>>(a);
 }
 template <int CIN, int COUT>
@@ -521,7 +575,7 @@ SceArgs sce_args(const float *params, const Layout &L, const linr_rows *rows) {
     return a;
 }
 
-void head_forward(const float *params, const Layout &L, const RowMap &m, int first_stage, int G, Tens x, float *hc,
+int head_forward(const float *params, const Layout &L, const RowMap &m, int first_stage, int G, Tens x, float *hc,
                   const uint8_t *occ, float *probs, uint16_t *cdf, float *dz, float dz_scale, float *bits_partial,
                   int stage_out_base, cudaStream_t s) {
     ConvArgs a = conv_args(m, params);
@@ -534,7 +588,7 @@ void head_forward(const float *params, const Layout &L, const RowMap &m, int fir
     a.y = hc ? T(hc, m.n_rows * 8, 8) : TN();
     a.occ = occ, a.stage_base = first_stage, a.stage_out_base = stage_out_base;
     a.probs = probs, a.cdf = cdf, a.dz = dz, a.dz_scale = dz_scale, a.bits_partial = bits_partial;
-    launch_conv<8, 8, 2>(a, G, s);
+    return launch_conv<8, 8, 2>(a, G, s);
 }
 
 int check_rows(const linr_rows *rows, int S, bool need_occ) {
@@ -638,11 +692,11 @@ int linr_net_forward(const float *d_params, int scale_num, const linr_rows *rows
     block_B_forward(d_params, L.ob, 7, m, w.ob_z, T(w.hh + R * 8, R * 8, 8), T(w.hh, 0, 8), s);
     // 8 heads
     const bool want_bits = d_bits != nullptr || train;
-    head_forward(d_params, L, m, 0, 8, T(w.hh, R * 8, 8), train ? w.hc : nullptr, rows->d_occ, d_probs, d_cdf,
-                 train ? w.dzs : nullptr, loss_scale * 1.4426950408889634f, want_bits ? w.bits_partial : nullptr, 0, s);
+    const int head_gx = head_forward(d_params, L, m, 0, 8, T(w.hh, R * 8, 8), train ? w.hc : nullptr, rows->d_occ, d_probs, d_cdf,
+                                     train ? w.dzs : nullptr, loss_scale * 1.4426950408889634f, want_bits ? w.bits_partial : nullptr, 0, s);
     if (d_bits) {
         ProfScope prof(K_REDUCE, 1, s);
-        bits_finalize_kernel<<<1, 256, 0, s>>>(w.bits_partial, (int)ceil_div64(R, (ConvCfg<8, 8, 2>::ROWS)) * 8, d_bits);
+        bits_finalize_kernel<<<1, 256, 0, s>>>(w.bits_partial, head_gx * 8, d_bits);
     }
     LINR_LAUNCH_CHECK();
     return LINR_OK;
@@ -856,8 +910,7 @@ int linr_spconv27_bwd_w(const float *d_x, int cin, const float *d_dy, int cout, 
     const int64_t R = rows->n_rows;
     const int P = 27 * cin * cout + cout;
     NetWs w;
-    w.n_chunks = chunks_for(R);
-    w.chunk = (ceil_div64(R > 0 ? R : 1, w.n_chunks) + BW_T - 1) / BW_T * BW_T;
+    set_chunks(w, R);
     LINR_REQUIRE(ws_bytes >= (size_t)w.n_chunks * P * sizeof(float), "linr_spconv27_bwd_w: workspace too small");
     w.partial = (float *)d_ws;
     const int wo[1] = {0}, bo[1] = {27 * cin * cout};

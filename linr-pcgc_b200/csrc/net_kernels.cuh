@@ -9,6 +9,7 @@
 // (no floating-point atomics anywhere -> bitwise reproducible run to run).
 #pragma once
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace linr {
 
@@ -27,6 +28,9 @@ struct RowMap {
     int64_t ld;
     const uint32_t *mask;
     int64_t n_rows;
+    const int32_t *tile_rng;    // [ceil(n_rows/128)][6] neighbour row ranges per 128-row tile (or null)
+    const int32_t *pair_cnt;    // [ceil(n_rows/256)][32] and
+    const uint32_t *pair_list;  // [ceil(n_rows/256)][27][256]: (row - tile base) << 24 | neighbour row (or null)
 };
 
 template <int C>
@@ -134,6 +138,47 @@ __device__ __forceinline__ u64 fadd2(u64 a, u64 b) {
     u64 d;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
+}
+
+// Plan of the staged ranges of one tile: combine the 128-row sub-tile ranges and lay the three dx ranges out back to
+// back (each starting on a 128-byte boundary of the staging area).  ok = false when the ranges do not fit.
+struct StagePlan {
+    int lo[3], len[3], base[3];
+    bool ok;
+    __device__ __forceinline__ int delta(int d) const { return base[d] - lo[d]; }  // staged row of neighbour row n = n + delta
+    __device__ __forceinline__ uint32_t bytes(int ld) const { return ok ? (uint32_t)(len[0] + len[1] + len[2]) * ld * 4u : 0u; }
+};
+__device__ __forceinline__ StagePlan plan_ranges(const int32_t *tile_rng, int64_t n_rows, int64_t row0, int tile_rows, int ld, int cap_bytes) {
+    StagePlan pl;
+    pl.ok = false;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) pl.lo[d] = 0, pl.len[d] = 0, pl.base[d] = 0;
+    if (!tile_rng) return pl;
+    int lo[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, hi[3] = {0, 0, 0};
+    const int64_t t0 = row0 >> 7, t1 = (min(row0 + tile_rows, n_rows) + 127) >> 7;
+    for (int64_t t = t0; t < t1; ++t) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const int l = tile_rng[t * 6 + 2 * d], h = tile_rng[t * 6 + 2 * d + 1];
+            if (h > l) lo[d] = min(lo[d], l), hi[d] = max(hi[d], h);
+        }
+    }
+    int tot = 0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (hi[d] <= lo[d]) lo[d] = 0, hi[d] = 0;
+        pl.lo[d] = lo[d], pl.len[d] = hi[d] - lo[d], pl.base[d] = tot;
+        tot += (pl.len[d] + 3) & ~3;
+    }
+    pl.ok = (int64_t)tot * ld * 4 <= cap_bytes;
+    return pl;
+}
+// Issue the bulk copies of a plan (the caller has armed `bar` with pl.bytes(ld) among its expected bytes).
+__device__ __forceinline__ void issue_ranges(const StagePlan &pl, const float *xg, int ld, float *sx, uint64_t *bar) {
+    if (!pl.ok) return;
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+        if (pl.len[d] > 0) bulk_g2s(sx + (int64_t)pl.base[d] * ld, xg + (int64_t)pl.lo[d] * ld, (uint32_t)pl.len[d] * ld * 4u, bar);
 }
 
 template <int CIN, int COUT, int MODE, bool CW = false>
@@ -467,8 +512,10 @@ struct BwdWArgs {
     float *partial;  // [n_chunks][P]
     int64_t P;
     int64_t chunk;  // rows per chunk (multiple of 32)
+    int no_xstage;  // v3: gather x through L1 instead of staging its row ranges
+    int groups;     // v3: a block walks its chunk once per group (one long TMA pipeline instead of `groups` short blocks)
 };
-constexpr int BW_T = 128;  // chunk granularity (rows)
+constexpr int BW_T = 256;  // chunk granularity (rows): whole pair-list tiles
 
 template <int CIN, int COUT, int MODE>
 struct BwdWCfg {
@@ -635,6 +682,287 @@ __global__ void __launch_bounds__(BwdWCfg<CIN, COUT, MODE>::TPB) __maxnreg__((Bw
             const int n = e / (CI * COUT), ci = (e / COUT) % CI, co = e % COUT;
             const int k = c + 9 * (j0 + n);
             if (ci < cin) out[a.w_off[g] + k * cin * COUT + ci * COUT + co] = v[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient, v3: staged + pair lists.  Same sums as conv27_bwd_w_kernel, different schedule:
+//  * a block owns one row chunk of one group and half of the 28 slots (27 offsets + bias), ONE WARP PER SLOT, plus a
+//    producer warp.  The chunk is walked in 256-row tiles through a ring of shared-memory stages that the producer
+//    fills with bulk (TMA) copies: the dy rows of the tile and the three neighbour row ranges of x
+//    (RowMap::tile_rng).  `full` mbarriers count the bytes of a stage, `empty` mbarriers the consumer warps that are
+//    done with it.  No block-wide barrier inside the loop.
+//  * a warp does not multiply by zero for absent neighbours: it walks the pair list of (tile, its offset)
+//    (RowMap::pair_list) 32 pairs at a time, every lane one (dy row, neighbour row) pair, both read from shared
+//    memory -- 14.3 of 27 slots are occupied on a surface, so this is ~1.9x fewer FMAs and loads than lane = row.
+//    Offsets differ in density (centre 1.0, faces .65, edges .51, corners .41): the slot -> warp table balances the
+//    sums per SM sub-partition (warp w runs on sub-partition w % 4).
+//  * lane-private dW[k] (CI x COUT, packed FFMA2) over the warp's pairs, transposing butterfly at the end of the chunk,
+//    one partial per (chunk, offset): fixed order, no floating-point atomics -> bitwise reproducible run to run.
+// ------------------------------------------------------------------------------------------------
+constexpr int BW3_NW = 14, BW3_T = 256;
+__constant__ int8_t c_bw3_slot[2][BW3_NW] = {
+    {1, 5, 12, 10, 3, 7, 14, 16, 0, 6, 9, 11, 2, 8},
+    {15, 19, 4, 13, 17, 21, 22, 24, 18, 23, 25, 26, 20, 27}};
+
+// DLD: row stride of dy in floats (COUT, or 8 when a 4-channel slice of an 8-wide tensor is the gradient)
+template <int CIN, int COUT, int MODE, int DLD>
+struct BwdW3Cfg {
+    static constexpr int CI = (MODE == 1) ? 7 : CIN;
+    static constexpr int XROWS = 1024;                                                   // staged neighbour rows per tile
+    static constexpr int XS = (MODE == 1) ? 0 : (XROWS + 8) * CIN * 4;                   // + a zero row for idle lanes
+    static constexpr int DYB = (BW3_T + 8) * DLD * 4;                                    // dy rows + a zero row
+    static constexpr int LSB = BW3_NW * 1024;                                            // the pair lists of the block's slots
+    static constexpr int STAGE = DYB + XS + LSB;
+    static constexpr int NST = (MODE == 1) ? 6 : 4;
+    static constexpr int SMEM = NST * STAGE + 256;
+    static constexpr int V = CI * COUT, VP = V <= 32 ? 32 : 64;
+    static_assert(STAGE % 128 == 0, "stages keep the 128-byte alignment of the bank swizzle");
+};
+
+// One staged row as raw 16-byte pieces.  8-channel rows are 32 bytes: eight consecutive rows would hit only four of
+// the eight 16-byte bank groups with their first halves, so rows 4..7 of every eight read their halves in the
+// opposite order (conflict-free for consecutive rows; resolved with two selects per half) ...
+template <int C>
+struct RawRow {
+    float4 u[C / 4];
+    int sw;
+};
+template <int C>
+__device__ __forceinline__ void raw_load(const float *base, int p, int ld, RawRow<C> &r) {
+    const float *q = base + p * ld;
+    if constexpr (C == 8) {
+        r.sw = (p >> 2) & 1;
+        r.u[0] = *reinterpret_cast<const float4 *>(q + 4 * r.sw);
+        r.u[1] = *reinterpret_cast<const float4 *>(q + 4 * (r.sw ^ 1));
+    } else {
+        r.sw = 0;
+        r.u[0] = *reinterpret_cast<const float4 *>(q);
+    }
+}
+// ... and in channel order
+template <int C>
+__device__ __forceinline__ void raw_resolve(const RawRow<C> &r, float (&v)[C]) {
+    if constexpr (C == 8) {
+        const float4 lo = r.sw ? r.u[1] : r.u[0], hi = r.sw ? r.u[0] : r.u[1];
+        v[0] = lo.x, v[1] = lo.y, v[2] = lo.z, v[3] = lo.w, v[4] = hi.x, v[5] = hi.y, v[6] = hi.z, v[7] = hi.w;
+    } else {
+        v[0] = r.u[0].x, v[1] = r.u[0].y, v[2] = r.u[0].z, v[3] = r.u[0].w;
+    }
+}
+
+template <int CIN, int COUT, int MODE, int DLD>
+__global__ void __launch_bounds__(32 * (BW3_NW + 1), 1) conv27_bwd_w3_kernel(const BwdWArgs a) {
+    using Cfg = BwdW3Cfg<CIN, COUT, MODE, DLD>;
+    constexpr int CI = Cfg::CI, HQ = COUT / 2, V = Cfg::V, VP = Cfg::VP, T = BW3_T, NST = Cfg::NST;
+    constexpr int XW = (MODE == 1) ? 1 : CIN;
+    extern __shared__ __align__(128) unsigned char bw3_smem[];
+    __shared__ int s_plan[NST][4];
+    uint64_t *full = reinterpret_cast<uint64_t *>(bw3_smem + NST * Cfg::STAGE), *empty = full + NST;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r0 = blockIdx.y * a.chunk;   // chunks are whole 256-row tiles
+    const int64_t r1 = min(r0 + a.chunk, a.map.n_rows);
+    const int n_tiles = r1 > r0 ? (int)((r1 - r0 + T - 1) / T) : 0;
+    const int n_vt = n_tiles * a.groups;        // virtual tiles: the chunk once per group, group-major
+    const int64_t tile0 = r0 / T;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NST; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], BW3_NW);
+        mbar_init_fence();
+    }
+    // zero rows (dy row T, x row XROWS of every stage): where idle lanes of a partial batch point
+    for (int i = threadIdx.x; i < NST * 8; i += blockDim.x) {
+        unsigned char *sb = bw3_smem + (i >> 3) * Cfg::STAGE;
+        if ((i & 7) < DLD) reinterpret_cast<float *>(sb)[T * DLD + (i & 7)] = 0.f;
+        if (MODE != 1 && (i & 7) < CIN) reinterpret_cast<float *>(sb + Cfg::DYB)[Cfg::XROWS * CIN + (i & 7)] = 0.f;
+    }
+    __syncthreads();
+
+    if (warp == BW3_NW) {   // ---- producer warp: NST - 1 tiles ahead of the slowest consumer
+        // lane w < 14 copies the pair list of consumer warp w's slot; lane 0 also plans and copies dy and the x ranges
+        const int my_slot = lane < BW3_NW ? c_bw3_slot[blockIdx.x][lane] : 27;
+        for (int vt = 0; vt < n_vt; ++vt) {
+            const int g = vt / n_tiles, t = vt - g * n_tiles;
+            const int st = vt % NST;
+            const int64_t row0 = r0 + (int64_t)t * T;
+            const int nrow = (int)min((int64_t)T, r1 - row0);
+            unsigned char *sb = bw3_smem + st * Cfg::STAGE;
+            // global reads first (they do not touch the stage), then wait for the stage to be free
+            const uint32_t lb = my_slot < 27 ? (uint32_t)((a.map.pair_cnt[(tile0 + t) * 32 + my_slot] + 3) & ~3) * 4u : 0u;
+            StagePlan pl;
+            pl.ok = false;
+            if constexpr (MODE != 1) {
+                if (lane == 0 && !a.no_xstage) pl = plan_ranges(a.map.tile_rng, a.map.n_rows, row0, T, CIN, Cfg::XROWS * CIN * 4);
+            }
+            uint32_t lsum = lb;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+            if (vt >= NST) mbar_wait(&empty[st], ((vt / NST) - 1) & 1);   // every consumer warp is done with virtual tile vt - NST
+            if (lane == 0) {
+                s_plan[st][0] = pl.ok ? pl.delta(0) : 0, s_plan[st][1] = pl.ok ? pl.delta(1) : 0, s_plan[st][2] = pl.ok ? pl.delta(2) : 0;
+                s_plan[st][3] = pl.ok;
+                const uint32_t dyb = (uint32_t)nrow * DLD * 4u;
+                mbar_arrive_expect_tx(&full[st], dyb + lsum + (MODE != 1 ? pl.bytes(CIN) : 0u));
+                bulk_g2s(sb, a.dy.p + g * a.dy.gs + a.dy.off + row0 * DLD, dyb, &full[st]);
+                if constexpr (MODE != 1) issue_ranges(pl, a.x.p + g * a.x.gs + a.x.off, CIN, reinterpret_cast<float *>(sb + Cfg::DYB), &full[st]);
+            }
+            __syncwarp();   // the barrier is armed before any other lane's copy can complete on it
+            if (lb) bulk_g2s(sb + Cfg::DYB + Cfg::XS + lane * 1024, a.map.pair_list + ((tile0 + t) * 27 + my_slot) * 256, lb, &full[st]);
+        }
+        return;
+    }
+
+    const int slot = c_bw3_slot[blockIdx.x][warp];
+    float *out = a.partial + blockIdx.y * a.P;
+    const bool is_bias = slot == 27;
+    const int dxi = slot % 3;   // offset k = slot = c + 9 j, dx index = c % 3 = k % 3
+    u64 acc[CI][HQ];
+#pragma unroll
+    for (int i = 0; i < CI; ++i)
+#pragma unroll
+        for (int q = 0; q < HQ; ++q) acc[i][q] = 0ull;
+
+    // FMAs of one pair per lane
+    auto fma_pair = [&](const float (&d)[COUT], const float (&xb)[XW]) {
+        u64 db[HQ];
+#pragma unroll
+        for (int q = 0; q < HQ; ++q) db[q] = pack2(d[2 * q], d[2 * q + 1]);
+#pragma unroll
+        for (int i = 0; i < CI; ++i) {
+            float xv;
+            if (MODE == 1) xv = ((__float_as_uint(xb[0]) >> i) & 1u) ? 1.f : 0.f;
+            else xv = xb[i];
+            const u64 xx = pack2(xv, xv);
+#pragma unroll
+            for (int q = 0; q < HQ; ++q) ffma2_acc(acc[i][q], xx, db[q]);
+        }
+    };
+    // end of a group's pass over the chunk: reduce the lane-private sums, store the partial, start over
+    auto flush = [&](int g) {
+        const int cin = (MODE == 1) ? (a.cin_base + g * a.cin_step) : CIN;
+        if (is_bias) {
+            if (a.b_off[g] >= 0) {
+                float v[COUT];
+#pragma unroll
+                for (int q = 0; q < HQ; ++q) unpack2(acc[0][q], v[2 * q], v[2 * q + 1]);
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) {
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) v[co] += __shfl_xor_sync(0xffffffffu, v[co], o);
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int co = 0; co < COUT; ++co) out[a.b_off[g] + co] = v[co];
+                }
+            }
+        } else {
+            float v[VP];
+#pragma unroll
+            for (int e = 0; e < VP; ++e) v[e] = 0.f;
+#pragma unroll
+            for (int i = 0; i < CI; ++i)
+#pragma unroll
+                for (int q = 0; q < HQ; ++q) unpack2(acc[i][q], v[i * COUT + 2 * q], v[i * COUT + 2 * q + 1]);
+            warp_transpose_reduce<VP>(v, lane);
+#pragma unroll
+            for (int i = 0; i < VP / 32; ++i) {
+                const int e = lane * (VP / 32) + i;
+                if (e < V) {
+                    const int ci = e / COUT, co = e % COUT;
+                    if (ci < cin) out[a.w_off[g] + slot * cin * COUT + ci * COUT + co] = v[i];
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < CI; ++i)
+#pragma unroll
+            for (int q = 0; q < HQ; ++q) acc[i][q] = 0ull;
+    };
+
+    if (n_tiles == 0) {   // a chunk past the end of the rows: its partials are zeros
+        for (int g = 0; g < a.groups; ++g) flush(g);
+        return;
+    }
+    int cnt_next = !is_bias ? a.map.pair_cnt[tile0 * 32 + slot] : 0;
+    int t = 0, g = 0;
+#pragma unroll 1
+    for (int vt = 0; vt < n_vt; ++vt) {
+        const int st = vt % NST;
+        const int cnt = cnt_next;
+        const int tn = (t + 1 == n_tiles) ? 0 : t + 1;
+        if (!is_bias) cnt_next = a.map.pair_cnt[(tile0 + tn) * 32 + slot];
+        mbar_wait(&full[st], (vt / NST) & 1);
+        const unsigned char *sb = bw3_smem + st * Cfg::STAGE;
+        const float *sdy = reinterpret_cast<const float *>(sb);
+        if (is_bias) {
+            const int64_t row0 = r0 + (int64_t)t * T;
+            const int nrow = (int)min((int64_t)T, r1 - row0);
+            for (int rl = lane; rl < nrow; rl += 32) {
+                RawRow<COUT> rr;
+                float d[COUT];
+                raw_load<COUT>(sdy, rl, DLD, rr);
+                raw_resolve<COUT>(rr, d);
+#pragma unroll
+                for (int q = 0; q < HQ; ++q) fadd2_acc(acc[0][q], pack2(d[2 * q], d[2 * q + 1]));
+            }
+        } else if ((MODE == 1) || s_plan[st][3]) {
+            // every operand in shared memory (MODE 1: the neighbour's occupancy byte comes from global memory).
+            // Software pipeline: the rows of batch b+1 are loaded before the FMAs of batch b.
+            const uint32_t *lst = reinterpret_cast<const uint32_t *>(sb + Cfg::DYB + Cfg::XS) + warp * 256;
+            const int dlt = s_plan[st][dxi];
+            const float *sx = reinterpret_cast<const float *>(sb + Cfg::DYB);
+            RawRow<COUT> rd;
+            RawRow<(MODE == 1) ? 4 : CIN> rx;
+            unsigned ob = 0;
+            auto load_batch = [&](int b) {
+                const bool on = b + lane < cnt;
+                const uint32_t e = on ? lst[b + lane] : 0u;
+                const int o = on ? (int)(e >> 24) : T;
+                raw_load<COUT>(sdy, o, DLD, rd);
+                if constexpr (MODE == 1) {
+                    ob = on ? (unsigned)a.occ[e & 0xffffffu] : 0u;
+                } else {
+                    const int n = on ? (int)(e & 0xffffffu) + dlt : Cfg::XROWS;
+                    raw_load<CIN>(sx, n, CIN, rx);
+                }
+            };
+            if (cnt > 0) load_batch(0);
+#pragma unroll 1
+            for (int b = 0; b < cnt; b += 32) {
+                float d[COUT], xb[XW];
+                raw_resolve<COUT>(rd, d);
+                if constexpr (MODE == 1) xb[0] = __uint_as_float(ob);
+                else raw_resolve<CIN>(rx, xb);
+                if (b + 32 < cnt) load_batch(b + 32);
+                fma_pair(d, xb);
+            }
+        } else {
+            // the neighbour ranges of this tile did not fit the staging area: gather x through L1
+            const uint32_t *lst = reinterpret_cast<const uint32_t *>(sb + Cfg::DYB + Cfg::XS) + warp * 256;
+            const float *xg = (MODE == 1) ? nullptr : (a.x.p + g * a.x.gs + a.x.off);
+#pragma unroll 1
+            for (int b = 0; b < cnt; b += 32) {
+                const bool on = b + lane < cnt;
+                const uint32_t e = on ? lst[b + lane] : 0u;
+                float d[COUT], xb[XW];
+                RawRow<COUT> rd;
+                raw_load<COUT>(sdy, on ? (int)(e >> 24) : T, DLD, rd);
+                raw_resolve<COUT>(rd, d);
+#pragma unroll
+                for (int i = 0; i < XW; ++i) xb[i] = 0.f;
+                if constexpr (MODE != 1) {
+                    if (on) gather_row<CIN>(xg + (int64_t)(e & 0xffffffu) * CIN, xb);
+                }
+                fma_pair(d, xb);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+        if (++t == n_tiles) {
+            flush(g);
+            t = 0, ++g;
         }
     }
 }

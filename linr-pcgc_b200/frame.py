@@ -14,6 +14,7 @@ About 54 B per row instead of the reference's pickled float tensors; a 32-frame 
 """
 from __future__ import annotations
 
+import ctypes as C
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -38,6 +39,9 @@ class RowTables:
     mask: torch.Tensor
     occ: Optional[torch.Tensor] = None
     nbr27: Optional[torch.Tensor] = None
+    tile_rng: Optional[torch.Tensor] = None   # int32 [ceil(R/128),6]: neighbour row ranges per tile (linr_tile_ranges)
+    pair_cnt: Optional[torch.Tensor] = None   # int32 [ceil(R/256),32] and
+    pair_list: Optional[torch.Tensor] = None  # int32 [ceil(R/256),27,256]: existing (row, neighbour) pairs per tile and offset
     table: Optional[torch.Tensor] = None   # open-addressing hash (kept only on request)
     cap: int = 0
     _rows: Optional[Rows] = field(default=None, repr=False)
@@ -54,12 +58,15 @@ class RowTables:
         r.d_anchor, r.d_mask = ptr(self.anchor), ptr(self.mask)
         r.d_nbr7, r.d_scale = ptr(self.nbr7), ptr(self.scale)
         r.d_occ = ptr(self.occ) if self.occ is not None else None
+        r.d_tile_rng = ptr(self.tile_rng) if self.tile_rng is not None else None
+        r.d_pair_cnt = ptr(self.pair_cnt) if self.pair_cnt is not None else None
+        r.d_pair_list = ptr(self.pair_list) if self.pair_list is not None else None
         self._rows = r
         return r
 
 
 def build_tables(coords: torch.Tensor, scale: torch.Tensor, occ: Optional[torch.Tensor] = None,
-                 dense: bool = False, keep_hash: bool = False) -> RowTables:
+                 dense: bool = False, keep_hash: bool = False, tile_ranges: bool = True) -> RowTables:
     """Hash the rows and build the 27-neighbour kernel map (replaces ME's coordinate manager)."""
     lib = _lib.load()
     assert coords.is_cuda and coords.dtype == torch.int32 and coords.dim() == 2 and coords.shape[1] == 3
@@ -72,13 +79,25 @@ def build_tables(coords: torch.Tensor, scale: torch.Tensor, occ: Optional[torch.
     check(lib.linr_hash_build(ptr(coords), ptr(scale), n, ptr(table), cap, s), "linr_hash_build")
     ld = (max(n, 1) + 31) // 32 * 32
     anchor = torch.empty((9, ld), dtype=torch.int32, device=dev)
-    mask = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    mask = torch.zeros(ld, dtype=torch.int32, device=dev)   # padded to ld: bulk copies read whole 16-byte pieces
     nbr7 = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
     nbr27 = torch.empty((n, 27), dtype=torch.int32, device=dev) if dense else None
     check(lib.linr_nbr_build(ptr(coords), ptr(scale), n, ptr(table), cap, ptr(nbr27) if dense else None, ptr(anchor), ld,
                              ptr(mask), ptr(nbr7), s), "linr_nbr_build")
-    return RowTables(coords=coords, scale=scale, nbr7=nbr7[:n] if n else nbr7[:0], anchor=anchor, mask=mask[:n] if n else mask[:0],
-                     occ=occ, nbr27=nbr27, table=table if (keep_hash or dense) else None, cap=cap)
+    t = RowTables(coords=coords, scale=scale, nbr7=nbr7[:n] if n else nbr7[:0], anchor=anchor, mask=mask[:n] if n else mask[:0],
+                  occ=occ, nbr27=nbr27, table=table if (keep_hash or dense) else None, cap=cap)
+    if n and tile_ranges:
+        rng = torch.empty(((n + 127) // 128, 6), dtype=torch.int32, device=dev)
+        rows = t.rows()
+        check(lib.linr_tile_ranges(C.byref(rows), ptr(rng), s), "linr_tile_ranges")
+        t.tile_rng = rng
+        if n < (1 << 24):
+            nt = (n + 255) // 256
+            t.pair_cnt = torch.empty((nt, 32), dtype=torch.int32, device=dev)
+            t.pair_list = torch.empty((nt, 27, 256), dtype=torch.int32, device=dev)
+            rows = t.rows()
+            check(lib.linr_pair_lists(C.byref(rows), ptr(t.pair_cnt), ptr(t.pair_list), s), "linr_pair_lists")
+    return t
 
 
 def hash_lookup(t: RowTables, query: torch.Tensor, query_scale: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -1,0 +1,121 @@
+"""GPU parity of the staged (bulk-copy / TMA) weight-gradient kernel and of the tables it reads.
+
+`linr_rows.d_tile_rng` + `d_pair_cnt` / `d_pair_list` switch the 8->8 weight gradient to conv27_bwd_w3_kernel
+(csrc/net_kernels.cuh): dy rows, neighbour row ranges and pair lists staged in shared memory by bulk copies, one
+(dy row, neighbour row) pair per lane.  The tables are integer work: bit-exact against a numpy restatement.  The
+gradient changes its summation schedule (compacted pairs), so it is compared within fp32 tolerance against the
+lane = row kernel and float64, and must stay bitwise reproducible run to run.  Forward results do not depend on the
+tables at all (the encoder / decoder reproducibility contract): checked bit for bit."""
+import dataclasses
+
+import numpy as np
+import pytest
+import torch
+
+from test_gpu_parity import L, O, _cuda, _load, _dense_from_compact, _net_case, RTOL  # noqa: F401  (fixtures)
+
+pytestmark = pytest.mark.gpu
+
+
+def _no_ranges(t):
+    return dataclasses.replace(t, tile_rng=None, pair_cnt=None, pair_list=None, _rows=None)
+
+
+def _ranges_from_dense(nb, n):
+    """numpy restatement of linr_tile_ranges on the dense [n,27] table."""
+    nt = (n + 127) // 128
+    out = np.zeros((nt, 6), dtype=np.int32)
+    for t in range(nt):
+        blk = nb[t * 128:(t + 1) * 128]
+        for d in range(3):
+            v = blk[:, [k for k in range(27) if k % 3 == d]]
+            v = v[v >= 0]
+            if len(v):
+                out[t, 2 * d], out[t, 2 * d + 1] = v.min(), v.max() + 1
+    return out
+
+
+@pytest.mark.parametrize("name", ["tiny", "ragged", "mid"])
+def test_tile_ranges_bit_exact(L, name):
+    g = _load(f"int_{name}.npz")
+    fr = L.frame.prepare_frame(_cuda(g["points"]), None, 64)
+    t = fr.tables
+    nb = _dense_from_compact(t.anchor, t.mask, t.n_rows)
+    assert t.tile_rng is not None and t.tile_rng.shape == ((t.n_rows + 127) // 128, 6)
+    np.testing.assert_array_equal(t.tile_rng.cpu().numpy(), _ranges_from_dense(nb, t.n_rows))
+
+
+@pytest.mark.parametrize("name", ["tiny", "ragged", "mid"])
+def test_pair_lists_bit_exact(L, name):
+    """linr_pair_lists: list (t,k) = rows of tile t with a neighbour at offset k, in row order, with that neighbour."""
+    g = _load(f"int_{name}.npz")
+    fr = L.frame.prepare_frame(_cuda(g["points"]), None, 64)
+    t = fr.tables
+    n = t.n_rows
+    nb = _dense_from_compact(t.anchor, t.mask, n)
+    cnt = t.pair_cnt.cpu().numpy()
+    lst = t.pair_list.cpu().numpy().view(np.uint32)
+    assert cnt.shape == ((n + 255) // 256, 32) and lst.shape == ((n + 255) // 256, 27, 256)
+    for ti in range(cnt.shape[0]):
+        blk = nb[ti * 256:(ti + 1) * 256]
+        for k in range(27):
+            rl = np.nonzero(blk[:, k] >= 0)[0]
+            assert cnt[ti, k] == len(rl)
+            want = (rl.astype(np.uint32) << np.uint32(24)) | blk[rl, k].astype(np.uint32)
+            np.testing.assert_array_equal(lst[ti, k, :len(rl)], want)
+        assert (cnt[ti, 27:] == 0).all()
+
+
+def _frames(L):
+    g = _load("int_mid.npz")
+    small = L.frame.prepare_frame(_cuda(g["points"]), None, 64)
+    big = L.frame.prepare_frame(L.synth.make_sequence("loot", 1, device="cuda")[0], None, 64)
+    return [("mid", small), ("loot", big)]
+
+
+def test_weight_gradient_v3_matches_v2_and_is_reproducible(L):
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    for name, fr in _frames(L):
+        t, t0 = fr.tables, _no_ranges(fr.tables)
+        n = t.n_rows
+        for cin, cout in ((8, 8), (8, 4), (4, 4)):
+            x = torch.randn(n, cin, generator=gen, device="cuda")
+            dy = torch.randn(n, cout, generator=gen, device="cuda")
+            dW, db = L.net.spconv27_bwd_w(x, dy, t)
+            dW2, db2 = L.net.spconv27_bwd_w(x, dy, t)
+            assert torch.equal(dW, dW2) and torch.equal(db, db2), (name, cin, cout)      # run to run bitwise
+            dW0, db0 = L.net.spconv27_bwd_w(x, dy, t0)
+            sc = dW0.abs().max().item()
+            assert (dW - dW0).abs().max().item() <= 2e-5 * sc, (name, cin, cout)         # fp32 re-association only
+            assert (db - db0).abs().max().item() <= 2e-5 * max(1.0, db0.abs().max().item())
+            # against float64 on the dense table
+            if name == "mid":
+                nb = torch.from_numpy(_dense_from_compact(t.anchor, t.mask, n)).cuda().long()
+                xd = torch.cat([x.double(), torch.zeros(1, cin, device="cuda", dtype=torch.float64)])
+                ref = torch.stack([xd[nb[:, k]].T @ dy.double() for k in range(27)])
+                assert (dW.double() - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+
+
+def test_network_staged_vs_gathered(L, O):
+    """Whole network: probabilities / CDFs bit-identical, gradient within fp32 re-association, training forward too."""
+    g, S, sd, flat, fr = _net_case(L, O)
+    cases = [(fr, flat.cuda())]
+    big = L.frame.prepare_frame(L.synth.make_sequence("mvub10", 1, device="cuda")[0], None, 64)
+    from linr_pcgc_b200 import params as P
+    cases.append((big, P.init_flat(big.n_scales, 11).cuda()))
+    for f, params in cases:
+        t, t0 = f.tables, _no_ranges(f.tables)
+        run = L.net.NetRunner(f.n_scales, t.n_rows, "cuda", train=True)
+        outs = []
+        for tab in (t, t0):
+            o = run.forward(params, tab, want_probs=True, want_cdf=True, want_bits=True)
+            probs, cdf = o["probs"].clone(), o["cdf"].clone()
+            grad = torch.empty_like(params)
+            run.forward(params, tab, train=True, loss_scale=1.0 / f.point_num)
+            run.backward(params, tab, grad)
+            outs.append((probs, cdf, grad.clone(), float(o["bits"].item())))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+        assert abs(outs[0][3] - outs[1][3]) <= 1e-6 * abs(outs[1][3])
+        ga, gb = outs[0][2], outs[1][2]
+        assert torch.isfinite(ga).all()
+        assert (ga - gb).abs().max().item() <= 5e-5 * gb.abs().max().item()
