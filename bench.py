@@ -3,16 +3,23 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
-A STEP is one GOP of the loot-shaped workload (BASELINE.json configs[1]): `--epochs` (10) passes of per-frame
-forward + backward + Adam over `--frames` (32) synthetic 10-bit frames of ~780k points, then 8-bit model
-quantisation and the real encode of every frame (network forward, 16-bit CDFs to the host, range coder).
-  value : inputs (prepared frames) resident in HBM when the timed region starts.
-  e2e   : the public API `pipeline.overfit_encode_gop` fed pinned HOST point arrays: H2D copy, octree/kernel-map
-          preparation, overfit, encode, bitstreams back on the host — all inside the timed region.
-N > 1 (torchrun): independent GOPs, one per GPU, no collective on the data path (weak scaling); `--dp` instead splits
-the frames of ONE GOP across ranks with an NCCL all-reduce of the 219 kB gradient per optimiser step.
-`--impl reference` times the CPU restatement of the reference (oracle/, torch CPU, all host threads) on a bounded
-sample of the same workload.
+A STEP is the whole north-star job (BASELINE.json configs[1] / configs[2]): a loot-shaped sequence of `--gops` (3) GOPs of
+`--frames` (32) synthetic 10-bit frames of ~780k points = 96 frames.  GOP 0 is overfitted first (`--epochs` (10) passes of
+per-frame forward + backward + Adam) because its parameters, Adam moments and learning rate seed the later GOPs
+(main.py:102-104); then the other GOPs; every GOP is followed by 8-bit model quantisation and the real encode of its frames
+(network forward, 16-bit CDFs to the host, range coder).
+  N = 1 : the three GOPs one after the other on one GPU.
+  N > 1 : dist.plan_job -- GOP 0 stage-split over all N GPUs (each rank computes its share of the 8 autoregressive stages of
+          every frame, ONE all-reduce of the flat 219 kB gradient per frame, identical fused Adam on every rank: the
+          reference's one-optimiser-step-per-frame semantics are kept), then GOPs 1 and 2 at the same time on two halves of
+          the GPUs, each stage-split over its half.  Fixed total work: "scaling": "strong".
+  value : inputs (prepared frames) resident in HBM when the timed region starts; whole-job seconds / 96 frames.
+  e2e   : the same job fed pinned HOST point arrays: H2D copy, octree / kernel-map preparation, overfit, encode, bitstreams
+          collected on rank 0 -- all inside the timed region.
+  replica: (extra key) the round-1 measure, one independent GOP per GPU with no collective (weak scaling).
+`--mode gop` times only that replica measure; `--decode-only` times BASELINE.json configs[4] (decode s/frame).
+`--impl reference` times the CPU restatement of the reference (oracle/, torch CPU, all host threads) on one whole
+frame-iteration + one frame encode of the same workload.
 """
 from __future__ import annotations
 
@@ -43,12 +50,15 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--shape", default="loot")
     ap.add_argument("--frames", type=int, default=32, help="GOP size (main.py --gop_size)")
+    ap.add_argument("--gops", type=int, default=None, help="GOPs of the sequence (default 3 = 96 frames; owlii: 2 = 64 frames)")
     ap.add_argument("--epochs", type=int, default=10, help="first_epoch / others_epoch of the north-star config")
-    ap.add_argument("--dp", action="store_true", help="intra-GOP data parallel instead of one GOP per GPU")
+    ap.add_argument("--mode", default="job", choices=["job", "gop"], help="job: the whole sequence; gop: one GOP per GPU (round-1 measure)")
+    ap.add_argument("--decode-only", action="store_true", help="BASELINE.json configs[4]: decode s/frame of an encoded GOP")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--gop-pipeline", action="store_true", help="code GOP i in the background while GOP i+1 is overfitted")
+    ap.add_argument("--no-extras", action="store_true", help="skip the replica measure and the C4 / C5 side configs")
     ap.add_argument("--cpu-sample-rows", type=int, default=75000)
+    ap.add_argument("--cpu-full-frame", action="store_true", help="cpu baseline on every scale of the frame (default for --impl reference)")
     return ap.parse_args()
 
 
@@ -91,8 +101,9 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ reference arm
 def oracle_sample(shape: str, sample_rows: int, threads: int):
-    """A bounded sample of one frame of the workload for the CPU restatement: the coarsest scales of one frame whose
-    parent-voxel count stays below `sample_rows` (cost is linear in voxel-passes; the ratio is reported)."""
+    """One frame of the workload for the CPU restatement.  sample_rows > 0: only the coarsest scales whose parent-voxel
+    count stays below `sample_rows` (a bounded sample; cost is linear in voxel-passes, the ratio is reported);
+    sample_rows <= 0: every scale."""
     from linr_pcgc_b200 import params as P, synth
     from oracle import linr_oracle as O
     torch.set_num_threads(threads)
@@ -102,7 +113,7 @@ def oracle_sample(shape: str, sample_rows: int, threads: int):
     total = sum(rows)
     keep, acc = [], 0
     for i in range(len(rows) - 1, -1, -1):
-        if acc + rows[i] > sample_rows and keep:
+        if sample_rows > 0 and acc + rows[i] > sample_rows and keep:
             break
         keep.append(i)
         acc += rows[i]
@@ -142,9 +153,12 @@ def oracle_encode(O, sub, nbrs, S, flat):
     return nbytes
 
 
-def cpu_reference_time(args, steps: int, warmup: int):
+def cpu_reference_time(args, steps: int, warmup: int, full: bool):
+    """s/frame of the CPU restatement = epochs x (one frame-iteration) + (one frame encode).  `full`: every scale of
+    the frame is timed (about 40 s per iteration on 16 cores); else a bounded sample of the coarsest scales, scaled
+    linearly in voxel-passes.  Both figures are kept apart in the returned dict."""
     threads = os.cpu_count() or 1
-    O, sub, nbrs, S, flat, rows, total, point_num = oracle_sample(args.shape, args.cpu_sample_rows, threads)
+    O, sub, nbrs, S, flat, rows, total, point_num = oracle_sample(args.shape, 0 if full else args.cpu_sample_rows, threads)
     m, v = torch.zeros_like(flat), torch.zeros_like(flat)
     scale = total / rows
     for i in range(warmup):
@@ -156,260 +170,448 @@ def cpu_reference_time(args, steps: int, warmup: int):
         its.append(time.perf_counter() - t0)
     t0 = time.perf_counter()
     oracle_encode(O, sub, nbrs, S, flat)
-    t_enc = time.perf_counter() - t0
-    t_iter = float(np.mean(its)) * scale
-    t_enc *= scale
+    t_enc_m = time.perf_counter() - t0
+    t_iter_m = float(np.mean(its))
+    t_iter, t_enc = t_iter_m * scale, t_enc_m * scale
     s_per_frame = args.epochs * t_iter + t_enc
-    sample = (f"oracle port (torch CPU), {rows} of {total} voxel-passes of one {args.shape} frame (coarsest scales), "
-              f"{steps} frame-iterations + 1 encode timed, scaled by {scale:.2f} to the full frame; "
-              f"s/frame = {args.epochs} x iter + encode")
-    return s_per_frame, t_iter, t_enc, threads, sample
+    what = "every scale" if full else "coarsest scales"
+    sample = (f"oracle port (torch CPU), {rows} of {total} voxel-passes of one {args.shape} frame ({what}), "
+              f"{steps} frame-iteration(s) + 1 encode timed: {t_iter_m:.2f} s/iteration, {t_enc_m:.2f} s/encode measured"
+              + ("" if full else f", scaled by {scale:.2f} to the full frame") + f"; s/frame = {args.epochs} x iteration + encode")
+    return {"value": s_per_frame, "iter_s": t_iter, "encode_s": t_enc, "iter_s_measured": t_iter_m, "encode_s_measured": t_enc_m,
+            "voxel_passes_timed": rows, "voxel_passes_frame": total, "threads": threads, "sample": sample}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
-    steps = min(steps, 3)  # each step is ~10 s of CPU work on the bounded sample
+    # one whole frame-iteration is ~40 s of CPU work: one timed iteration per step, at most two steps, no warm-up pass
+    steps = max(1, min(args.steps, 2))
     t_all0 = time.perf_counter()
-    v, t_iter, t_enc, threads, sample = cpu_reference_time(args, steps, warmup)
-    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": v * args.frames * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+    r = cpu_reference_time(args, steps, 0, full=True)
+    G = args.gops or (2 if args.shape == "owlii" else 3)
+    line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["value"] * args.frames * G * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": workload_config(args, 1),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "iter_s": t_iter, "encode_s": t_enc, "wall_s": time.perf_counter() - t_all0}
+            "config": workload_config(args, 1, G),
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "iter_s": r["iter_s"], "encode_s": r["encode_s"], "wall_s": time.perf_counter() - t_all0,
+            "note": "CPU restatement of the reference (the reference's own natives, MinkowskiEngine / torchac, are not installable "
+                    "offline); a whole frame-iteration is timed, s/frame is iteration x epochs + encode -- context, not a speed-up "
+                    "over the reference's GPU path"}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, n):
-    from linr_pcgc_b200 import synth
+def workload_config(args, n, G):
+    from linr_pcgc_b200 import dist as D, synth
     bits, pts = synth.SHAPES[args.shape]
-    cfg = {"loot": "BASELINE.json configs[1]", "owlii": "BASELINE.json configs[3] (per-GPU share)",
+    cfg = {"loot": "BASELINE.json configs[1] (N=1) / configs[2] (N>1)", "owlii": "BASELINE.json configs[3]",
            "plumbing": "BASELINE.json configs[0]"}.get(args.shape, "parity-test shape")
+    if args.mode == "gop":
+        par = "gop%d (one independent GOP per GPU, no collective)" % n
+    elif n == 1:
+        par = "1 GPU, GOPs one after the other"
+    else:
+        ph = D.plan_job(G, n)
+        par = ("GOP 0 stage-split over %d GPUs (gradient all-reduce per frame), then %s" %
+               (len(ph[0][0][0]), "; ".join("GOPs %s stage-split over GPUs %d-%d" % (g, r[0], r[-1]) for r, g in ph[1]) if len(ph) > 1 else "-"))
     return {"workload": f"{args.shape}-shaped synthetic {bits}-bit surface, ~{pts // 1000}k pts/frame, gop_size {args.frames}, "
-                        f"{args.epochs} epochs/GOP, overfit + model quantisation + encode ({cfg})",
-            "gop_size": args.frames, "epochs": args.epochs, "frames_per_step": args.frames * (1 if args.dp else n),
-            "parallelism": ("dp%d (frames of one GOP split, NCCL all-reduce of gradients)" % n) if args.dp and n > 1
-            else ("gop%d (one GOP per GPU, no collective)" % n),
-            "gop_pipeline": "coding of GOP i overlaps overfitting of GOP i+1 (all K GOPs coded inside the timed region)" if args.gop_pipeline else "serial",
+                        f"{G} GOPs = {G * args.frames} frames, {args.epochs} epochs/GOP, overfit + model quantisation + encode ({cfg})",
+            "gop_size": args.frames, "gops": G, "epochs": args.epochs,
+            "frames_per_step": args.frames * (n if args.mode == "gop" else G),
+            "parallelism": par,
             "l2_policy": "inputs larger than L2: one GOP's resident tables + activations >> 126 MB L2"}
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
-def main():
-    args = parse()
-    if args.impl == "reference":
-        return run_reference(args)
+class Ctx:
+    """Everything the measures share: process group, devices, library handles."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    import torch.distributed as dist
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    def __init__(self, args):
+        self.args = args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        import torch.distributed as dist
+        self.dist = dist
+        from linr_pcgc_b200 import dist as D
+        self.D = D
+        self.cores = D.bind_rank_cores()
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        from linr_pcgc_b200 import _lib
+        self.lib = _lib.load()
 
-    from linr_pcgc_b200 import _lib, pipeline, synth
-    from linr_pcgc_b200.net import NetRunner
-    from linr_pcgc_b200.trainer import GopTrainer
-    lib = _lib.load()
-
-    F, E = args.frames, args.epochs
-    if args.dp and world > 1:
-        my = list(range(rank, F, world))       # frames of ONE GOP split across ranks
-        start = 0
-    else:
-        my = list(range(F))                    # one GOP per rank
-        start = rank * F
-    seq = synth.make_sequence(args.shape, F, device=dev, start=start)
-    pts_dev = [seq[i] for i in my]
-    pts_host = [p.cpu().pin_memory() for p in pts_dev]
-    frames = pipeline.prepare_gop(pts_dev, None, 64, dev)
-    S = frames[0].n_scales
-    rows = [f.tables.n_rows for f in frames]
-    max_rows = max(rows)
-
-    grad_hook = None
-    if args.dp and world > 1:
-        def grad_hook(g):
-            dist.all_reduce(g)   # sum of per-frame gradients; every rank then takes the same Adam step
-    tr = GopTrainer(S, dev, seed=8807, max_rows=max_rows, grad_hook=grad_hook)
-    run = NetRunner(S, max_rows, dev, train=False)
-
-    # --gop-pipeline: the coding of the GOP of step i (side stream + host coder threads) overlaps the overfitting of
-    # the GOP of step i+1; `timed` collects the last one before it closes the timed region, so K steps = K GOPs fully
-    # overfitted AND coded.  Measured round 1: -1 % on resident inputs, +4 % end to end (the coder's host threads
-    # compete with the launch thread) -> off by default, every step is strictly serial.
-    coder = pipeline.GopCoder(dev) if args.gop_pipeline else None
-
-    def step_resident():
-        tr.fit(frames, E)
-        if coder is not None:
-            return coder.submit(frames, tr.state.params, S)
-        return pipeline.encode_gop(frames, tr.state.params, S, 8, runner=run)
-
-    state = {"s": None}
-
-    def step_e2e():
-        enc, st, _ = pipeline.overfit_encode_gop(pts_host, E, state=state["s"], device=dev, seed=8807,
-                                                 trainer_kwargs={"grad_hook": grad_hook}, coder=coder)
-        state["s"] = st
-        return enc
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, prof_mask=0):
-        lib.linr_prof_enable(prof_mask)
-        barrier()
+    def timed(self, fn, steps, prof_mask=0):
+        """K calls of fn bracketed by barrier + synchronize on both sides; device time (CUDA events), max over ranks."""
+        self.lib.linr_prof_enable(prof_mask)
+        self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
         out = None
         for _ in range(steps):
             out = fn()
-        if coder is not None and hasattr(out, "result"):
-            out = coder.collect()     # the last GOP's bitstreams; orders this stream after the coder's
         e1.record()
-        barrier()
+        self.barrier()
         wall = time.perf_counter() - t0
         ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item()), wall, out
 
-    def prof_table():
+    def prof_table(self):
         import ctypes as C
         tab = []
-        for c in range(lib.linr_prof_classes()):
+        for c in range(self.lib.linr_prof_classes()):
             ms, n, u = C.c_double(), C.c_int64(), C.c_int64()
-            lib.linr_prof_read(c, C.byref(ms), C.byref(n), C.byref(u))
-            tab.append({"kernel": lib.linr_prof_name(c).decode(), "ms": ms.value, "launches": n.value, "units": u.value})
+            self.lib.linr_prof_read(c, C.byref(ms), C.byref(n), C.byref(u))
+            tab.append({"kernel": self.lib.linr_prof_name(c).decode(), "ms": ms.value, "launches": n.value, "units": u.value})
         return tab
 
-    # warm-up: W untimed steps; the last one runs with every kernel class bracketed by events -> breakdown
-    W, K = max(args.warmup, 0), max(args.steps, 1)
-    for i in range(W):
-        if i == W - 1:
-            _, _, _ = timed(step_resident, 1, prof_mask=(1 << lib.linr_prof_classes()) - 1)
-            breakdown = prof_table()
-        else:
-            step_resident()
-            if coder is not None:
-                coder.collect()
-    if W == 0:
-        breakdown = []
-    dom = max(range(len(breakdown)), key=lambda c: breakdown[c]["ms"]) if breakdown else 0
+    def all_mask(self):
+        return (1 << self.lib.linr_prof_classes()) - 1
 
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    ms, wall, enc = timed(step_resident, K, prof_mask=1 << dom)
-    live = prof_table()
-    clk = clocks.stop() if rank == 0 else None
-    launches = sum(r["launches"] for r in live)
 
-    # roofline of the dominant kernel class, measured live in the timed region
-    mask_pop = 0.0
+def mean_occupied(frames):
+    pop = 0.0
     for f in frames[:4]:
         m = f.tables.mask.to(torch.int64) & 0x7FFFFFF
         cnt = torch.zeros_like(m)
         for b in range(27):
             cnt += (m >> b) & 1
-        mask_pop += float(cnt.double().mean().item())
-    pbar = mask_pop / max(1, len(frames[:4]))
-    d = live[dom]
-    bytes_per_unit = algorithmic_bytes(d["kernel"], pbar)
+        pop += float(cnt.double().mean().item())
+    return pop / max(1, len(frames[:4]))
+
+
+def roofline_of(d, pbar, step_ms):
+    """Roofline entry of one kernel class from its live CUDA-event time (measured in the timed region)."""
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = (bytes_per_unit * d["units"]) / max(d["ms"], 1e-9) / 1e6 if d["launches"] else 0.0  # GB/s
-    roofline = {"bound": "hbm", "kernel": d["kernel"], "achieved": achieved, "peak": peak,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
-                "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (NCU_DRAM_BYTES_PER_UNIT[d["kernel"]] * d["units"] / max(1, d["launches"])
-                            if d["kernel"] in NCU_DRAM_BYTES_PER_UNIT else None),
-                "traffic_source": "ncu --set full dram bytes per (row x group) unit, profiles/r01e_*, r01g_*; scaled by this run's units per launch",
-                "launches": d["launches"], "avg_launch_us": 1e3 * d["ms"] / max(1, d["launches"]),
-                "algorithmic_bytes_per_launch": bytes_per_unit * d["units"] / max(1, d["launches"]),
-                "mean_occupied_neighbours": pbar,
-                "share_of_step": d["ms"] / max(ms, 1e-9)}
+    bpu = algorithmic_bytes(d["kernel"], pbar)
+    achieved = (bpu * d["units"]) / max(d["ms"], 1e-9) / 1e6 if d["launches"] else 0.0  # GB/s
+    return {"bound": "hbm", "kernel": d["kernel"], "achieved": achieved, "peak": peak,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+            "unit": "GB/s", "frac": achieved / peak,
+            "traffic": (NCU_DRAM_BYTES_PER_UNIT[d["kernel"]] * d["units"] / max(1, d["launches"])
+                        if d["kernel"] in NCU_DRAM_BYTES_PER_UNIT else None),
+            "traffic_source": NCU_TRAFFIC_SOURCE,
+            "launches": d["launches"], "avg_launch_us": 1e3 * d["ms"] / max(1, d["launches"]),
+            "algorithmic_bytes_per_launch": bpu * d["units"] / max(1, d["launches"]),
+            "mean_occupied_neighbours": pbar, "share_of_step": d["ms"] / max(step_ms, 1e-9)}
 
-    # end to end through the public API with host buffers
-    e2e = None
-    if not args.no_e2e:
-        for _ in range(min(W, 1)):
-            step_e2e()
-            if coder is not None:
-                coder.collect()
-        ms_e, _, enc_e = timed(step_e2e, K)
-        n_frames_job = F if (args.dp and world > 1) else F * world
-        h2d = sum(int(p.numel()) * 4 for p in pts_host)
-        d2h = sum(r * (8 * 2 + 1) for r in rows) + 8 * len(rows) * E + 54712
-        e2e = {"value": ms_e / 1e3 / K / n_frames_job, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
 
-    # decode the whole GOP outside the headline region: lossless check (decoder.py:140) + decode throughput
-    lossless, decode_s = None, None
-    if rank == 0:
-        nd = min(len(frames), 16)
-        sub = pipeline.EncodedGop(enc.scale_num, enc.side_info, enc.model_bytes, enc.model_bits,
-                                  pipeline.codec.pack_low_xyz([f.scale_coords(S - 1).cpu().numpy() for f in frames[:nd]],
-                                                              [f.coord_min for f in frames[:nd]]),
-                                  enc.frame_bytes[:nd], enc.point_nums[:nd])
-        pipeline.decode_gop(sub, dev)                      # warm-up (allocations, streams)
-        decode_s = float("inf")
-        for _ in range(2):                                 # host-thread scheduling makes single runs noisy: best of two
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            dec = pipeline.decode_gop(sub, dev)
-            torch.cuda.synchronize()
-            decode_s = min(decode_s, (time.perf_counter() - t0) / nd)
-        lossless = all(bool(d.shape == p.shape and (d == p).all()) for d, p in zip(dec, pts_dev[:nd]))
+class Job:
+    """The whole sequence on this rank's share of the schedule (dist.plan_job)."""
 
-    n_frames_job = F if (args.dp and world > 1) else F * world
-    value = ms / 1e3 / K / n_frames_job
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": False, "scaling": "strong" if (args.dp and world > 1) else "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
-            "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-            "overfit_iters_per_s": None, "bpp": enc.bpp, "decode_lossless": lossless, "decode_s_per_frame": decode_s,
-            "points_per_frame": int(np.mean(enc.point_nums)), "voxel_passes_per_frame": int(np.mean(rows)),
+    def __init__(self, cx: Ctx, shape: str, F: int, G: int, E: int):
+        from linr_pcgc_b200 import pipeline, synth
+        from linr_pcgc_b200.net import NetRunner
+        from linr_pcgc_b200.trainer import GopTrainer
+        self.cx, self.shape, self.F, self.G, self.E = cx, shape, F, G, E
+        D, dev, rank = cx.D, cx.dev, cx.rank
+        self.phases = D.plan_job(G, cx.world)
+        D.make_groups(self.phases)
+        self.mine = []      # (gop, ranks) in execution order
+        for phase in self.phases:
+            for ranks, gops in phase:
+                if rank in ranks:
+                    self.mine += [(g, ranks) for g in gops]
+        self.pts_dev = {g: synth.make_sequence(shape, F, device=dev, start=g * F) for g, _ in self.mine}
+        self.pts_host = {g: [p.cpu().pin_memory() for p in v] for g, v in self.pts_dev.items()}
+        g0 = self.mine[0][0]
+        first = pipeline.prepare_gop(self.pts_dev[g0][:1], None, 64, dev)[0]
+        self.S = first.n_scales
+        if cx.world > 1:     # every rank must agree on the scale count (discovered from frame 0 of GOP 0, main.py:77-78)
+            t = torch.tensor([self.S if g0 == 0 else 0], device=dev)
+            cx.dist.all_reduce(t, op=cx.dist.ReduceOp.MAX)
+            self.S = int(t.item())
+        self.frames = {g: pipeline.prepare_gop(v, self.S, 64, dev) for g, v in self.pts_dev.items()}
+        self.max_rows = max(f.tables.n_rows for v in self.frames.values() for f in v)
+        self.runner = NetRunner(self.S, self.max_rows, dev, train=False)
+        self.trainers = {}
+        for g, ranks in self.mine:
+            key = tuple(ranks)
+            if key not in self.trainers:
+                self.trainers[key] = GopTrainer(self.S, dev, seed=8807, max_rows=self.max_rows,
+                                                stages=D.stage_range(len(ranks), ranks.index(rank)), group=D.group_for(ranks))
+        self.pipeline = pipeline
+
+    def step(self, from_host: bool = False, encode: bool = True):
+        """One whole job; returns {gop: EncodedGop} for the GOPs whose group this rank leads."""
+        cx, D = self.cx, self.cx.D
+        out, state0 = {}, None
+        for g, ranks in self.mine:
+            frames = self.pipeline.prepare_gop(self.pts_host[g], self.S, 64, cx.dev) if from_host else self.frames[g]
+            tr = self.trainers[tuple(ranks)]
+            if g == 0:
+                tr.reset(seed=8807)
+            else:
+                tr.reset(state=state0.clone())          # later GOPs start from GOP 0's state (main.py:102-104,241-246)
+            tr.fit(frames, self.E)
+            if g == 0:
+                state0 = tr.state.clone() if len(self.mine) > 1 else tr.state
+            if encode:
+                enc = self.pipeline.encode_gop_shared(frames, tr.state.params, self.S, 8, self.runner, ranks, D.group_for(ranks))
+                if enc is not None:
+                    out[g] = enc
+        return out
+
+    def h2d_bytes(self):
+        return sum(int(p.numel()) * 4 for v in self.pts_host.values() for p in v)
+
+    def d2h_bytes(self):
+        rows = [f.tables.n_rows for v in self.frames.values() for f in v]
+        return sum(r * (8 * 2 + 1) for r in rows) + 8 * len(rows) * self.E + 54712 * len(self.frames)
+
+
+def decode_check(cx, pipeline, enc, frames, pts_dev, S, nd=16):
+    """Decode the first frames of a GOP outside the headline region: lossless check (decoder.py:140) + throughput."""
+    nd = min(len(frames), nd)
+    sub = pipeline.EncodedGop(enc.scale_num, enc.side_info, enc.model_bytes, enc.model_bits,
+                              pipeline.codec.pack_low_xyz([f.scale_coords(S - 1).cpu().numpy() for f in frames[:nd]],
+                                                          [f.coord_min for f in frames[:nd]]),
+                              enc.frame_bytes[:nd], enc.point_nums[:nd])
+    pipeline.decode_gop(sub, cx.dev)                      # warm-up (allocations, streams)
+    best = float("inf")
+    for _ in range(2):                                    # host-thread scheduling makes single runs noisy: best of two
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dec = pipeline.decode_gop(sub, cx.dev)
+        torch.cuda.synchronize()
+        best = min(best, (time.perf_counter() - t0) / nd)
+    lossless = all(bool(d.shape == p.shape and (d == p).all()) for d, p in zip(dec, pts_dev[:nd]))
+    return lossless, best, sub
+
+
+def run_job(cx: Ctx, args, shape, G, K, W, e2e=True, with_checks=True):
+    """Headline measure: the whole sequence.  Returns the JSON line (dict) on every rank (rank 0's is printed)."""
+    F, E = args.frames, args.epochs
+    job = Job(cx, shape, F, G, E)
+    n_frames = F * G
+    breakdown = []
+    for i in range(W):
+        if i == W - 1:
+            cx.timed(job.step, 1, prof_mask=cx.all_mask())
+            breakdown = cx.prof_table()
+        else:
+            job.step()
+    dom = max(range(len(breakdown)), key=lambda c: breakdown[c]["ms"]) if breakdown else 0
+    clocks = ClockSampler(cx.local)
+    if cx.rank == 0:
+        clocks.start()
+    ms, wall, enc = cx.timed(job.step, K, prof_mask=1 << dom)
+    live = cx.prof_table()
+    clk = clocks.stop() if cx.rank == 0 else None
+    launches = sum(r["launches"] for r in live)
+    first_frames = job.frames[job.mine[0][0]]
+    pbar = mean_occupied(first_frames)
+    line = {"metric": METRIC, "value": ms / 1e3 / K / n_frames, "unit": UNIT, "n_gpus": cx.world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": None, "clocks": clk, "e2e": None, "gpu_launches": launches,
+            "roofline": roofline_of(live[dom], pbar, ms) if live else None,
             "kernel_breakdown_ms_per_step": {r["kernel"]: round(r["ms"], 3) for r in breakdown if r["launches"]},
-            "wall_s_timed": wall}
+            "wall_s_timed": wall, "host_cores_per_rank": cx.cores or (os.cpu_count() or 0)}
+    if e2e:
+        for _ in range(min(W, 1)):
+            job.step(from_host=True)
+        Ke = min(K, 3)
+        ms_e, _, _ = cx.timed(lambda: job.step(from_host=True), Ke)
+        ms_e *= K / Ke   # scaled to K steps below; the e2e region is timed over min(K, 3) whole jobs
+        io = torch.tensor([job.h2d_bytes(), job.d2h_bytes()], dtype=torch.float64, device=cx.dev)
+        if cx.world > 1:
+            cx.dist.all_reduce(io)
+        line["e2e"] = {"value": ms_e / 1e3 / K / n_frames, "unit": UNIT, "h2d_bytes_per_step": int(io[0].item()),
+                       "d2h_bytes_per_step": int(io[1].item()), "steps": Ke}
+        # what the e2e - resident difference is made of: per-frame upload + octree / kernel-map / pair-list preparation
+        tabs = first_frames[0].tables
+        prep_bytes = sum(int(t.numel()) * t.element_size() for t in (tabs.coords, tabs.anchor, tabs.mask, tabs.nbr7, tabs.occ, tabs.scale,
+                                                                        tabs.tile_rng, tabs.pair_cnt, tabs.pair_list) if t is not None)
+        d_ms = (ms_e - ms) / K / n_frames
+        line["roofline_prep"] = {"bound": "hbm", "stage": "frame preparation (H2D + sort/unique + hash + kernel map + pair lists)",
+                                 "ms_per_frame": d_ms, "table_bytes_per_frame": prep_bytes,
+                                 "achieved": prep_bytes / max(d_ms, 1e-9) / 1e6, "unit": "GB/s", "peak": line["roofline"]["peak"] if line["roofline"] else None,
+                                 "frac": (prep_bytes / max(d_ms, 1e-9) / 1e6) / line["roofline"]["peak"] if line["roofline"] else None,
+                                 "note": "table bytes written per frame / (e2e - resident) time; sort passes and hash probes re-read them several times"}
+    # phase timings (one extra untimed-for-the-headline pass each): GOP 0's fit, whole-job fit, encode
+    if with_checks:
+        ms_fit, _, _ = cx.timed(lambda: job.step(encode=False), 1)
+        line["overfit_iters_per_s"] = n_frames * E / (ms_fit / 1e3)          # frame-iterations (fwd+bwd+Adam) per second, whole job
+        line["encode_s_per_frame"] = max(0.0, (ms / K - ms_fit)) / 1e3 / n_frames
+        g0, ranks0 = job.mine[0]
+        tr0 = job.trainers[tuple(ranks0)]
+        tr0.reset(seed=8807)
+        ms_g0, _, _ = cx.timed(lambda: tr0.fit(job.frames[g0], 1), 1)
+        line["gop0_iters_per_s"] = F / (ms_g0 / 1e3)                          # GOP 0: every rank on the same frame
+        line["gop0_split"] = len(ranks0)
+    if cx.rank == 0 and enc:
+        line["bpp"] = {f"gop{g}": e.bpp for g, e in sorted(enc.items())}
+        line["points_per_frame"] = int(np.mean(enc[0].point_nums))
+        line["voxel_passes_per_frame"] = int(np.mean([f.tables.n_rows for f in first_frames]))
+        if with_checks:
+            lossless, dec_s, _ = decode_check(cx, job.pipeline, enc[0], job.frames[0], job.pts_dev[0], job.S)
+            line["decode_lossless"], line["decode_s_per_frame"] = lossless, dec_s
+    return line, job
 
-    # overfit-only and encode-only split (one extra untimed-for-the-headline pass each)
-    ms_fit, _, _ = timed(lambda: tr.fit(frames, 1), 1)
-    ms_enc, _, _ = timed(lambda: pipeline.encode_gop(frames, tr.state.params, S, 8, runner=run), 1)
-    line["overfit_iters_per_s"] = n_frames_job / (ms_fit / 1e3)   # frame-iterations (fwd+bwd+Adam) per second, whole job
-    line["encode_s_per_frame"] = ms_enc / 1e3 / n_frames_job
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+def run_replica(cx: Ctx, args, K, W):
+    """Round-1 measure: one independent GOP per GPU, no collective (weak scaling)."""
+    from linr_pcgc_b200 import pipeline, synth
+    from linr_pcgc_b200.net import NetRunner
+    from linr_pcgc_b200.trainer import GopTrainer
+    F, E = args.frames, args.epochs
+    pts = synth.make_sequence(args.shape, F, device=cx.dev, start=cx.rank * F)
+    frames = pipeline.prepare_gop(pts, None, 64, cx.dev)
+    S = frames[0].n_scales
+    mr = max(f.tables.n_rows for f in frames)
+    tr = GopTrainer(S, cx.dev, seed=8807, max_rows=mr)
+    run = NetRunner(S, mr, cx.dev, train=False)
+
+    def step():
+        tr.fit(frames, E)
+        return pipeline.encode_gop(frames, tr.state.params, S, 8, runner=run)
+
+    breakdown = []
+    for i in range(W):
+        if i == W - 1:
+            cx.timed(step, 1, prof_mask=cx.all_mask())
+            breakdown = cx.prof_table()
+        else:
+            step()
+    ms, wall, enc = cx.timed(step, K)
+    return {"value": ms / 1e3 / K / (F * cx.world), "unit": UNIT, "scaling": "weak", "steps": K, "ms_per_step": ms / K,
+            "frames_per_step": F * cx.world, "parallelism": "gop%d (one independent GOP per GPU, no collective)" % cx.world,
+            "bpp": enc.bpp, "kernel_breakdown_ms_per_step": {r["kernel"]: round(r["ms"], 3) for r in breakdown if r["launches"]}}, (frames, pts, enc, S, tr, run)
+
+
+def run_decode_only(cx: Ctx, args, shape, F=16, E=3, K=3, W=1):
+    """BASELINE.json configs[4]: decode-only throughput (deterministic inference + host arithmetic decoding) of an
+    MVUB-shaped GOP, bit-exact reconstruction checked.  The GOP is overfitted for a few epochs and encoded outside the
+    timed region; a step decodes all its frames (codec.decode_frames: one host thread + stream per frame in flight)."""
+    from linr_pcgc_b200 import pipeline, synth
+    from linr_pcgc_b200.trainer import GopTrainer
+    pts = synth.make_sequence(shape, F, device=cx.dev, start=cx.rank * F)
+    frames = pipeline.prepare_gop(pts, None, 64, cx.dev)
+    S = frames[0].n_scales
+    tr = GopTrainer(S, cx.dev, seed=8807, max_rows=max(f.tables.n_rows for f in frames))
+    tr.fit(frames, E)
+    enc = pipeline.encode_gop(frames, tr.state.params, S, 8)
+    for _ in range(W):
+        pipeline.decode_gop(enc, cx.dev)
+    cx.lib.linr_prof_enable(cx.all_mask())
+    cx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        dec = pipeline.decode_gop(enc, cx.dev)
+    cx.barrier()
+    wall = time.perf_counter() - t0          # the decoder's streams belong to its worker threads: host clock around a full sync
+    tab = cx.prof_table()
+    t = torch.tensor([wall], dtype=torch.float64, device=cx.dev)
+    if cx.world > 1:
+        cx.dist.all_reduce(t, op=cx.dist.ReduceOp.MAX)
+    wall = float(t.item())
+    lossless = all(bool(d.shape == p.shape and (d == p).all()) for d, p in zip(dec, pts))
+    rows = float(np.mean([f.tables.n_rows for f in frames]))
+    s_frame = wall / K / (F * cx.world)
+    conv_ms = sum(r["ms"] for r in tab if r["kernel"].startswith("conv27"))
+    fwd_bytes = 7950.0 * rows                                   # SURVEY.md 8(d): forward-only algorithmic bytes per voxel-pass
+    peak = roofline_of({"kernel": "conv27<8,8>", "units": 0, "ms": 1, "launches": 0}, 14.3, 1.0)["peak"]
+    return {"metric": "decode_s_per_frame", "value": s_frame, "unit": UNIT, "shape": shape, "frames": F * cx.world, "steps": K,
+            "lossless": lossless, "bpp": enc.bpp, "points_per_frame": int(np.mean(enc.point_nums)), "voxel_passes_per_frame": int(rows),
+            "frames_in_flight": min(16, F), "gpu_launches": sum(r["launches"] for r in tab),
+            "roofline": {"bound": "hbm", "kernel": "sequential 8-stage inference (all conv27 classes)", "unit": "GB/s",
+                         "achieved_wall": fwd_bytes / s_frame / 1e9, "achieved_kernels": fwd_bytes * F * K / max(conv_ms, 1e-9) / 1e6,
+                         "peak": peak, "frac_wall": fwd_bytes / s_frame / 1e9 / peak,
+                         "frac_kernels": fwd_bytes * F * K / max(conv_ms, 1e-9) / 1e6 / peak,
+                         "note": "wall: host range decoder + 56 device<->host round trips per frame included; kernels: CUDA-event time of the conv launches only"}}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    cx = Ctx(args)
+    W, K = max(args.warmup, 0), max(args.steps, 1)
+    G = args.gops or (2 if args.shape == "owlii" else 3)
+
+    if args.decode_only:
+        line = run_decode_only(cx, args, args.shape, F=min(args.frames, 16), E=min(args.epochs, 3), K=K, W=max(1, min(W, 2)))
+        line.update({"n_gpus": cx.world, "higher_is_better": False, "dtype": "f32", "data": "synthetic",
+                     "config": {"workload": f"{args.shape}-shaped decode-only (BASELINE.json configs[4])"}})
+        if cx.rank == 0:
+            print(json.dumps(line), flush=True)
+        return finish(cx)
+
+    if args.mode == "gop":
+        rep, (frames, pts, enc, S, tr, run) = run_replica(cx, args, K, W)
+        line = {"metric": METRIC, "value": rep["value"], "unit": UNIT, "n_gpus": cx.world, "steps": K, "warmup": W,
+                "ms_per_step": rep["ms_per_step"], "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": workload_config(args, cx.world, G), "bpp": rep["bpp"],
+                "kernel_breakdown_ms_per_step": rep["kernel_breakdown_ms_per_step"]}
+        if cx.rank == 0:
+            print(json.dumps(line), flush=True)
+        return finish(cx)
+
+    line, job = run_job(cx, args, args.shape, G, K, W, e2e=not args.no_e2e)
+    line["config"] = workload_config(args, cx.world, G)
+    if not args.no_extras:
+        rep, _ = run_replica(cx, args, 1, 1)
+        line["replica"] = rep
+        extras = {}
         try:
-            v, t_iter, t_enc, threads, sample = cpu_reference_time(args, 1, 0)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+            if cx.world == 1 and args.shape == "loot":
+                del job
+                torch.cuda.empty_cache()
+                for shp in ("mvub10", "mvub9"):      # C5: decode-only throughput
+                    extras[f"C5_decode_{shp}"] = run_decode_only(cx, args, shp, F=16, E=3, K=2, W=1)
+            if cx.world == 8 and args.shape == "loot":
+                del job
+                torch.cuda.empty_cache()
+                a2 = argparse.Namespace(**vars(args))
+                a2.shape = "owlii"
+                l2, j2 = run_job(cx, a2, "owlii", 2, 1, 1, e2e=False, with_checks=False)   # C4: Owlii 64 frames on 8 GPUs
+                l2["config"] = workload_config(a2, cx.world, 2)
+                extras["C4_owlii_64_frames"] = {k: l2[k] for k in ("value", "unit", "ms_per_step", "steps", "scaling", "config", "bpp",
+                                                                 "points_per_frame", "voxel_passes_per_frame", "roofline") if k in l2}
+        except Exception as ex:   # side configs never take the headline down
+            extras["error"] = repr(ex)
+        line["side_configs"] = extras
+    if cx.rank == 0 and cx.world == 1 and not args.no_cpu_baseline:
+        try:
+            r = cpu_reference_time(args, 1, 0, full=args.cpu_full_frame)
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": r["sample"]}
         except Exception as ex:  # the baseline is reported, never load-bearing
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
-    if rank == 0:
+    if cx.rank == 0:
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    finish(cx)
+
+
+def finish(cx):
+    if cx.world > 1:
+        cx.dist.barrier()
+        cx.dist.destroy_process_group()
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE 8-group launch over a loot-shaped frame (277,011 rows x 8 groups
 # = 2,216,088 units), from the `ncu --set full` captures summarised under profiles/ (r01e conv kernels, r01g weight
 # gradients); per unit, so it scales to the launches of this run.  None: not captured.
+NCU_TRAFFIC_SOURCE = "ncu --set full dram bytes per (row x group) unit, profiles/r01e_*, r01g_*; scaled by this run's units per launch"
 NCU_DRAM_BYTES_PER_UNIT = {
     "conv27<8,8>": (83.960832e6 + 39.300096e6) / 2216088, "conv27<8,4>": (82.984704e6 + 18.523136e6) / 2216088,
     "conv27<4,4>": (173.155072e6 + 58.067968e6) / 2216088, "conv27_bits<8>": (11.316992e6 + 6.055936e6) / 1939077,

@@ -159,6 +159,21 @@ int linr_net_forward(const float *d_params, int scale_num, const linr_rows *rows
 int linr_net_backward(const float *d_params, int scale_num, const linr_rows *rows, float *d_grad, void *d_ws,
                       size_t ws_bytes, void *stream);
 
+/* The same two passes restricted to the stages [stage_lo, stage_hi) of the 8 (a "stage split" of ONE frame over several
+ * GPUs, SURVEY.md 8(e)(i): the reference steps the optimiser once per frame, main.py:305-321, so frames cannot be dealt
+ * to ranks without changing the result; the 8 stages of a frame can).  A rank runs SCE + block_in (replicated), the LDFE
+ * blocks outter_blocks[k-1] and the heads k of ITS stages (models/upsample.py:203-216).  _forward_stages: d_probs / d_cdf
+ * rows of other stages are left untouched, d_bits is the bit count of the range.  _backward_stages: d_grad is overwritten
+ * with the gradient contribution of the range -- zeros for the parameters of other stages, and for SCE / block_in the
+ * part that flows through this range's dg = sum_k dh_k (the backward pass is linear in dg).  The SUM over a partition
+ * of [0,8) equals linr_net_backward's gradient up to fp32 summation order: one all-reduce(sum) of the flat 219 kB
+ * vector, then the same fused Adam step on every rank. */
+int linr_net_forward_stages(const float *d_params, int scale_num, const linr_rows *rows, int stage_lo, int stage_hi, int train,
+                            float loss_scale, float *d_probs, uint16_t *d_cdf, double *d_bits, void *d_ws, size_t ws_bytes,
+                            void *stream);
+int linr_net_backward_stages(const float *d_params, int scale_num, const linr_rows *rows, int stage_lo, int stage_hi,
+                             float *d_grad, void *d_ws, size_t ws_bytes, void *stream);
+
 /* Sequential decoding (CNP.decode, models/upsample.py:249-295), one coordinate set at a time:
  *  _begin: SCE + block_in (GDFE);  _stage k: [LDFE_{k-1} on the k bits decoded so far] + SConv_k + MLP_k
  *  -> d_cdf_stage[n_rows] (+ d_probs_stage optional).  rows->d_occ must hold stages < k. */

@@ -158,7 +158,7 @@ def decode_scale(runner: NetRunner, params: torch.Tensor, coords: torch.Tensor, 
     ctx.reserve(n)
     scale = torch.full((n,), scale_idx, dtype=torch.uint8, device=dev)
     occ = torch.zeros(n, dtype=torch.uint8, device=dev)
-    t = build_tables(coords, scale, occ)
+    t = build_tables(coords, scale, occ, tile_ranges=False)   # forward only: the gradient kernels' tables are not needed
     streams = unpack_bitstream(data)
     d_sym = torch.empty(n, dtype=torch.uint8, device=dev)
     # the eight device<->host round trips of the scale run inside one C call (no interpreter lock held), so the frames

@@ -2,7 +2,8 @@
 
     python -m linr_pcgc_b200.main --overfit True --encode True --decode True --ori_dir <plys> --frame_num 96 \
         --gop_size 32 --first_epoch 10 --others_epoch 10 --result_dir out --encode_dir enc --decode_dir dec
-    torchrun --nproc-per-node 8 -m linr_pcgc_b200.main ...        # GOPs sharded over GPUs (linr_pcgc_b200.dist)
+    torchrun --nproc-per-node 8 -m linr_pcgc_b200.main ...        # GOP 0 stage-split over all GPUs, then the other GOPs on
+                                                                   # groups of GPUs (linr_pcgc_b200.dist.plan_job)
 
 Every flag of the reference is accepted with the same name, type and default (booleans are the strings
 'True'/'False' as there); `--synthetic <shape>` replaces `--ori_dir` by the seeded generator of synth.py.  Outputs
@@ -69,7 +70,6 @@ def build_parser() -> argparse.ArgumentParser:
     # additions of this implementation
     p.add_argument("--synthetic", type=str, default=None, help="generate the sequence with synth.py (loot, owlii, mvub9, ...)")
     p.add_argument("--apply_seed", type=str, default="False", help="seed the parameter init with --seed (the reference never seeds)")
-    p.add_argument("--dp_first_gop", type=str, default="False", help="train GOP 0 data-parallel over all ranks")
     return p
 
 
@@ -123,20 +123,29 @@ def load_checkpoint(path: str, device) -> (OptimState, int):
 
 
 def overfit_one_gop(args, seq: Sequence, group: List[int], epochs: int, seed_state: Optional[OptimState], device,
-                    data_parallel: bool = False):
-    """main.py:122-455 for one GOP; returns (OptimState, scale_num)."""
+                    ranks: Optional[List[int]] = None):
+    """main.py:122-455 for one GOP; returns (OptimState, scale_num).  `ranks`: the ranks that share this GOP -- each
+    computes its stages of every frame (dist.stage_range), one gradient all-reduce per frame; the first one writes."""
     name = f"gop_{group[0]}_{group[-1]}"
     gdir = os.path.join(args.result_dir, name)
     os.makedirs(gdir, exist_ok=True)
-    my = [group[i] for i in D.frame_shard(len(group), D.world(), D.rank())] if data_parallel else group
-    frames = pipeline.prepare_gop(seq.points(my), args.scale_num, args.min_point_num, device)
+    ranks = ranks if ranks and len(ranks) > 1 else None
+    parts, part = (len(ranks), ranks.index(D.rank())) if ranks else (1, 0)
+    pg = D.group_for(ranks) if ranks else None
+    writer = ranks is None or part == 0
+    frames = pipeline.prepare_gop(seq.points(group), args.scale_num, args.min_point_num, device)
     S = args.scale_num or frames[0].n_scales
     args.scale_num = S
-    hook = D.GradAllReduce() if data_parallel and D.world() > 1 else None
-    tr = GopTrainer(S, device, args.learning_rate, args.gamma, args.step_size, args.min_lr, args.decay_rate,
-                    seed=args.seed if args.apply_seed == "True" else None,
+    seed = args.seed if args.apply_seed == "True" else None
+    if seed_state is None and ranks and seed is None:
+        # the reference never seeds (main.py:504 is parsed and unused); the members of a stage split must still start
+        # from ONE random model: the first rank draws the seed
+        t = torch.randint(0, 2 ** 31 - 1, (1,), device=device)
+        torch.distributed.broadcast(t, ranks[0], group=pg)
+        seed = int(t.item())
+    tr = GopTrainer(S, device, args.learning_rate, args.gamma, args.step_size, args.min_lr, args.decay_rate, seed=seed,
                     state=seed_state.clone() if seed_state is not None else None,
-                    max_rows=max(f.tables.n_rows for f in frames), grad_hook=hook)
+                    max_rows=max(f.tables.n_rows for f in frames), stages=D.stage_range(parts, part), group=pg)
     results, t_train = [], 0.0
     for ep in range(epochs):
         torch.cuda.synchronize()
@@ -145,16 +154,16 @@ def overfit_one_gop(args, seq: Sequence, group: List[int], epochs: int, seed_sta
         torch.cuda.synchronize()
         t_train += time.time() - t0
         rec = {"epoch": ep, "loss": loss, "train_time": t_train, "train_time_avg": t_train / len(group)}
-        if args.mid_test == "True" and (ep < 10 or ep % args.check_freq == 0):
+        if args.mid_test == "True" and writer and (ep < 10 or ep % args.check_freq == 0):
             enc = pipeline.encode_gop(frames, tr.state.params, S, args.model_bitdepth)
             rec.update({"real_bpp_all": enc.bpp, "model_bpp": enc.model_bits / sum(enc.point_nums),
                         "xyzlow_bpp": 8 * len(enc.low_enc_bytes) / sum(enc.point_nums), "enc_mode": enc.side_info["enc_mode"]})
         results.append(rec)
         logger.info(f"{name} epoch {ep} loss {loss:.5f} train_time {t_train:.2f}s lr {tr.state.lr:.3e}")
-        if D.rank() == 0 or not data_parallel:
+        if writer:
             with open(os.path.join(gdir, "result.json"), "w") as f:
                 json.dump(results, f, indent=4)
-    if args.write_pth == "True" and (D.rank() == 0 or not data_parallel):
+    if args.write_pth == "True" and writer:
         save_checkpoint(os.path.join(gdir, "model.pth"), tr.state, S, epochs - 1, results[-1]["loss"] if results else 0.0,
                         args.model_bitdepth)
     return tr.state, S
@@ -171,32 +180,35 @@ def run(args) -> None:
     seq = Sequence(args, device)
     groups = gop_ranges(args.frame_num, args.gop_size)
     names = [f"gop_{g[0]}_{g[-1]}" for g in groups]
-    mine = [0] + D.plan_gops(len(groups), D.world())[D.rank()]   # GOP 0 first, then this rank's share of the rest
+    phases = D.plan_job(len(groups), D.world())
+    D.make_groups(phases)
+    # GOPs whose files this rank writes: the first rank of the group that trained them
+    mine = [g for phase in phases for ranks, gops in phase for g in gops if ranks[0] == D.rank()]
 
     if args.overfit == "True":
         seed_state = None
         if args.pretrain_path and os.path.exists(str(args.pretrain_path)):
             seed_state, args.scale_num = load_checkpoint(args.pretrain_path, device)
-        dp0 = args.dp_first_gop == "True" and D.world() > 1
-        if dp0 or D.rank() == 0:
-            state0, S = overfit_one_gop(args, seq, groups[0], args.first_epoch, seed_state, device, data_parallel=dp0)
-        else:
-            n = P.offsets(P.param_spec(args.scale_num or 7))[-1]
-            state0 = OptimState(torch.empty(n, device=device), torch.empty(n, device=device), torch.empty(n, device=device), 0, 0, 0.0)
-        if D.world() > 1 and not dp0:
+        first = phases[0][0][0]
+        state0 = None
+        if D.rank() in first:
+            state0, S = overfit_one_gop(args, seq, groups[0], args.first_epoch, seed_state, device, ranks=first)
+        if D.world() > len(first):   # more ranks than one GOP can use: ship GOP 0's state to the others
             sn = torch.tensor([args.scale_num or 0], device=device)
             torch.distributed.broadcast(sn, 0)
             args.scale_num = int(sn.item())
-            n = P.offsets(P.param_spec(args.scale_num))[-1]
-            if D.rank() != 0:
+            if state0 is None:
+                n = P.offsets(P.param_spec(args.scale_num))[-1]
                 state0 = OptimState(torch.empty(n, device=device), torch.empty(n, device=device), torch.empty(n, device=device), 0, 0, 0.0)
             state0 = D.broadcast_state(state0, 0)
-        for g in mine[1:]:
-            overfit_one_gop(args, seq, groups[g], args.others_epoch, state0, device)
+        for ranks, gops in (phases[1] if len(phases) > 1 else []):
+            if D.rank() in ranks:
+                for g in gops:
+                    overfit_one_gop(args, seq, groups[g], args.others_epoch, state0, device, ranks=ranks)
         if D.world() > 1:
             torch.distributed.barrier()
 
-    todo = [g for g in mine if g != 0 or D.rank() == 0]
+    todo = mine
     if args.encode == "True":
         for g in todo:
             st, S = load_checkpoint(os.path.join(args.result_dir, names[g], "model.pth"), device)

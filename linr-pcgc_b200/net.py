@@ -49,17 +49,19 @@ class NetRunner:
 
     # -- teacher-forced forward over all 8 stages ---------------------------------------------------------
     def forward(self, params: torch.Tensor, t: RowTables, train: bool = False, loss_scale: float = 0.0,
-                want_probs: bool = False, want_cdf: bool = False, want_bits: bool = True):
+                want_probs: bool = False, want_cdf: bool = False, want_bits: bool = True, stages=(0, 8)):
+        """`stages` = (lo, hi): only the stages lo..hi-1 (one rank's share of a stage split, linr_net_forward_stages)."""
         assert params.is_cuda and params.dtype == torch.float32 and params.numel() == self.P
         assert t.occ is not None, "teacher-forced forward needs the ground-truth occupancy"
         assert not train or self.train, "runner was created without training workspace"
         n = t.n_rows
         self.reserve(n)
         rows = t.rows()
-        check(self.lib.linr_net_forward(ptr(params), self.S, C.byref(rows), 1 if train else 0, loss_scale,
-                                        ptr(self.probs) if want_probs else None, ptr(self.cdf) if want_cdf else None,
-                                        ptr(self.bits) if want_bits else None, ptr(self.ws), self.ws.numel(), stream_ptr()),
-              "linr_net_forward")
+        check(self.lib.linr_net_forward_stages(ptr(params), self.S, C.byref(rows), int(stages[0]), int(stages[1]),
+                                               1 if train else 0, loss_scale,
+                                               ptr(self.probs) if want_probs else None, ptr(self.cdf) if want_cdf else None,
+                                               ptr(self.bits) if want_bits else None, ptr(self.ws), self.ws.numel(), stream_ptr()),
+              "linr_net_forward_stages")
         out = {}
         if want_bits:
             out["bits"] = self.bits
@@ -69,11 +71,11 @@ class NetRunner:
             out["cdf"] = self.cdf[: 8 * n].view(8, n)
         return out
 
-    def backward(self, params: torch.Tensor, t: RowTables, grad: torch.Tensor):
-        assert grad.is_cuda and grad.numel() == self.P
+    def backward(self, params: torch.Tensor, t: RowTables, grad: torch.Tensor, stages=(0, 8)):
+        assert grad.is_cuda and grad.numel() >= self.P
         rows = t.rows()
-        check(self.lib.linr_net_backward(ptr(params), self.S, C.byref(rows), ptr(grad), ptr(self.ws), self.ws.numel(),
-                                         stream_ptr()), "linr_net_backward")
+        check(self.lib.linr_net_backward_stages(ptr(params), self.S, C.byref(rows), int(stages[0]), int(stages[1]), ptr(grad),
+                                                ptr(self.ws), self.ws.numel(), stream_ptr()), "linr_net_backward_stages")
 
     # -- sequential decode ----------------------------------------------------------------------------------
     def decode_begin(self, params: torch.Tensor, t: RowTables):

@@ -73,6 +73,35 @@ def encode_gop(frames: Sequence[Frame], flat_params: torch.Tensor, scale_num: in
     return EncodedGop(scale_num, side, comp["final_bytes"], comp["bit_real"], low, frame_bytes, [f.point_num for f in frames])
 
 
+def encode_gop_shared(frames: Sequence[Frame], flat_params: torch.Tensor, scale_num: int, bitdepth: int = 8,
+                      runner: Optional[NetRunner] = None, ranks: Optional[Sequence[int]] = None, group=None) -> Optional[EncodedGop]:
+    """encode_gop with the frames of the GOP dealt to the `ranks` that trained it together (every member holds the same
+    parameters bit for bit after a stage-split fit): member p codes frames p, p + parts, ...; the first rank collects the
+    bitstreams and returns the EncodedGop, the others return None."""
+    import torch.distributed as dist
+    if not ranks or len(ranks) == 1:
+        return encode_gop(frames, flat_params, scale_num, bitdepth, runner=runner)
+    part = list(ranks).index(dist.get_rank())
+    comp = model_compression.compress_model(flat_params, bitdepth)
+    if runner is None:
+        runner = NetRunner(scale_num, max(f.tables.n_rows for f in frames), flat_params.device, train=False)
+    mine = list(range(part, len(frames), len(ranks)))
+    coded = codec.encode_frames(runner, comp["recon_ret"], [frames[i] for i in mine])
+    box = [None] * len(ranks) if part == 0 else None
+    dist.gather_object(list(zip(mine, coded)), box, dst=ranks[0], group=group)
+    if part != 0:
+        return None
+    frame_bytes: List = [None] * len(frames)
+    for share in box:
+        for i, fb in share:
+            frame_bytes[i] = fb
+    lows = [f.scale_coords(f.n_scales - 1).cpu().numpy() for f in frames]
+    low = codec.pack_low_xyz(lows, [f.coord_min for f in frames])
+    side = dict(mu=comp["mu"], b=comp["b"], min_param=comp["min_param"], max_param=comp["max_param"],
+                enc_mode=comp["enc_mode"], bitdepth=bitdepth)
+    return EncodedGop(scale_num, side, comp["final_bytes"], comp["bit_real"], low, frame_bytes, [f.point_num for f in frames])
+
+
 def decode_gop(enc: EncodedGop, device="cuda", workers: Optional[int] = None) -> List[torch.Tensor]:
     """decode_one_gop (decoder.py:51-147): model from its bitstream, frames coarse-to-fine; returns the original
     (min-restored) sorted coordinates of every frame as CUDA int32 [Np,3]."""

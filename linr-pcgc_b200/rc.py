@@ -20,6 +20,12 @@ def host_cores() -> int:
     per GPU share the host; LOCAL_WORLD_SIZE is absent in single-process runs)."""
     n = os.cpu_count() or 8
     try:
+        aff = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        aff = n
+    if aff < n:
+        return max(2, aff - 1)     # the rank was bound to a slice of the cores (dist.bind_rank_cores): one stays with the launch thread
+    try:
         n //= max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
     except ValueError:
         pass

@@ -156,9 +156,23 @@ def test_sharding_plans():
     assert D.plan_gops(3, 2) == [[1], [2]]
     assert D.plan_gops(3, 8)[:3] == [[1], [2], []]
     assert D.plan_gops(4, 2, first_is_seed=False) == [[0, 2], [1, 3]]
-    sh = [D.frame_shard(5, 2, r) for r in range(2)]
-    assert sh == [[0, 2, 4], [1, 3, 0]] and len(sh[0]) == len(sh[1])
-    assert sorted(set(sum([D.frame_shard(32, 8, r) for r in range(8)], []))) == list(range(32))
+    # stage split: contiguous, disjoint, covering [0,8) for every group size
+    for parts in range(1, 9):
+        rs = [D.stage_range(parts, p) for p in range(parts)]
+        assert rs[0][0] == 0 and rs[-1][1] == 8 and all(a[1] == b[0] for a, b in zip(rs, rs[1:])) and all(lo < hi for lo, hi in rs)
+    assert [D.stage_range(8, p) for p in (0, 7)] == [(0, 1), (7, 8)] and D.stage_range(2, 1) == (4, 8)
+    with pytest.raises(ValueError):
+        D.stage_range(9, 0)
+    # the 96-frame / gop-32 job of BASELINE.json configs[2]: GOP 0 on every rank first, then GOPs 1, 2 on two halves
+    assert D.plan_job(3, 8) == [[(list(range(8)), [0])], [([0, 1, 2, 3], [1]), ([4, 5, 6, 7], [2])]]
+    assert D.plan_job(3, 4) == [[([0, 1, 2, 3], [0])], [([0, 1], [1]), ([2, 3], [2])]]
+    assert D.plan_job(3, 2) == [[([0, 1], [0])], [([0], [1]), ([1], [2])]]
+    assert D.plan_job(3, 1) == [[([0], [0])], [([0], [1, 2])]]
+    assert D.plan_job(2, 8) == [[(list(range(8)), [0])], [(list(range(8)), [1])]]          # Owlii: 64 frames = 2 GOPs
+    assert D.plan_job(1, 4) == [[([0, 1, 2, 3], [0])]]
+    ph = D.plan_job(6, 3)
+    assert sorted(g for _, gops in ph[1] for g in gops) == [1, 2, 3, 4, 5] and [r for r, _ in ph[1]] == [[0], [1], [2]]
+    assert sorted(sum([D.frame_share(32, 4, p) for p in range(4)], [])) == list(range(32))
 
 
 def _free_port():
@@ -180,10 +194,16 @@ def _worker(rank, world, port, out):
         st = OptimState(torch.empty(n), torch.empty(n), torch.empty(n), 0, 0, 0.0)
     st = D.broadcast_state(st, 0)
     ok = bool((st.params == torch.arange(n, dtype=torch.float32)).all()) and st.step == 17 and st.sched_step == 19 and st.lr == 1.25e-3
-    hook = D.GradAllReduce()
+    # sub-groups of a plan_job schedule: created collectively, a singleton group needs no communicator
+    phases = D.plan_job(3, world)
+    D.make_groups(phases)
+    ok = ok and D.group_for([0, 1]) is None and D.group_for([rank]) is not None
     g = torch.full((n,), float(rank + 1))
-    hook(g)                                              # mean over ranks of (1, 2) = 1.5 on every rank
-    ok = ok and bool((g == 1.5).all()) and hook.calls == 1
+    dist.all_reduce(g, group=D.group_for(phases[0][0][0]))   # the stage-split gradient sum over GOP 0's ranks
+    ok = ok and bool((g == 3.0).all())
+    g1 = torch.full((4,), float(rank + 1))
+    dist.all_reduce(g1, group=D.group_for([rank]))           # phase 1: one rank per GOP, nothing crosses ranks
+    ok = ok and bool((g1 == float(rank + 1)).all())
     gathered = D.gather_bytes([bytes([rank])] * 2)
     if rank == 0:
         ok = ok and gathered == [[b"\x00", b"\x00"], [b"\x01", b"\x01"]]
