@@ -38,6 +38,27 @@ const char *linr_last_error(void);
 /* device properties the host side needs for grid sizing (SM count, L2 bytes). Synchronous. */
 int linr_device_info(int device, int *sm_count, int64_t *l2_bytes);
 
+/* Contexts ("no global state except an opaque, explicitly created/destroyed linr_ctx* per device").
+ * A context stands for one user of a device -- one trainer, one coder -- driven by one host thread at a time;
+ * linr_ctx_set_current binds it to the calling host thread, and entry points called with no current context use a
+ * per-device default context (never destroyed).  What a context carries: its turn at the device's constant weight
+ * bank and its launch statistics.  The training kernels read their conv weights from the bank; a training call
+ * (linr_net_forward with train != 0, linr_net_backward) holds the bank from its first fill to its end, then records an
+ * event on its stream; the next holder -- any context, any stream -- makes its stream wait for that event before it
+ * fills the bank, so trainers that run one after the other all use the fast kernels, and a trainer that finds the bank
+ * held by a call of ANOTHER host thread runs the shared-memory kernel variant for that call (same bits).
+ * linr_ctx_destroy waits for the context's last training call if its weights are still the bank's contents.
+ * Everything else a call needs travels in its arguments; the SM count is cached per device; the profiler below is
+ * process-wide by design (bench.py reads one table).
+ *  linr_ctx_bank_calls / linr_ctx_bank_launches (NULL = the calling thread's current context): training calls that
+ *  held the bank, and constant-bank conv launches made, through the context. */
+typedef struct linr_ctx linr_ctx;
+int linr_ctx_create(int device, linr_ctx **out);
+int linr_ctx_destroy(linr_ctx *ctx);
+int linr_ctx_set_current(linr_ctx *ctx);
+int64_t linr_ctx_bank_calls(const linr_ctx *ctx);
+int64_t linr_ctx_bank_launches(const linr_ctx *ctx);
+
 /* Launch accounting / live kernel timing (no reference counterpart: the reference has no profiler hooks,
  * SURVEY.md section 5).  Kernel classes are the K_* values of csrc/prof.cuh; linr_prof_name() names them.
  *  linr_prof_enable(mask): bit c set -> launches of class c are bracketed by CUDA events on their stream
@@ -219,6 +240,10 @@ int linr_adam_fused(float *d_params, const float *d_grad, float *d_m, float *d_v
  *  d_q u8[n] symbols, d_recon f32[n] dequantised, d_stats float[4] = {min, max, mu, b}. bitdepth <= 8. */
 int linr_param_quant(const float *d_params, int64_t n, int bitdepth, uint8_t *d_q, float *d_recon, float *d_stats,
                      void *stream);
+/* The same with 16-bit symbols, bitdepth <= 16 (`--model_bitdepth` 9..16: the reference quantises these but cannot decode
+ * them, model_compression/model_size_est.py:546-548 reads the symbols back as uint8). */
+int linr_param_quant16(const float *d_params, int64_t n, int bitdepth, uint16_t *d_q, float *d_recon, float *d_stats,
+                       void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Host range coder (stays on the CPU by design; replaces torchac.encode_float_cdf / decode_float_cdf,

@@ -31,6 +31,11 @@ SIGNATURES = {
     "linr_version": (_I, []),
     "linr_last_error": (C.c_char_p, []),
     "linr_device_info": (_I, [_I, C.POINTER(_I), C.POINTER(_I64)]),
+    "linr_ctx_create": (_I, [_I, C.POINTER(_P)]),
+    "linr_ctx_destroy": (_I, [_P]),
+    "linr_ctx_set_current": (_I, [_P]),
+    "linr_ctx_bank_calls": (_I64, [_P]),
+    "linr_ctx_bank_launches": (_I64, [_P]),
     "linr_prof_enable": (_I, [C.c_uint32]),
     "linr_prof_read": (_I, [_I, C.POINTER(C.c_double), C.POINTER(_I64), C.POINTER(_I64)]),
     "linr_prof_classes": (_I, []),
@@ -65,6 +70,7 @@ SIGNATURES = {
     "linr_spconv27_bwd_w": (_I, [_P, _I, _P, _I, _RP, _P, _P, _P, _SZ, _P]),
     "linr_adam_fused": (_I, [_P, _P, _P, _P, _I64, _I64, _F, _F, _F, _F, _F, _P]),
     "linr_param_quant": (_I, [_P, _I64, _I, _P, _P, _P, _P]),
+    "linr_param_quant16": (_I, [_P, _I64, _I, _P, _P, _P, _P]),
     "linr_rc_encode_binary": (_I64, [_P, _P, _I64, _P, _I64]),
     "linr_rc_decode_binary": (_I, [_P, _P, _I64, _P, _I64]),
     "linr_rc_encode_binary_batch": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _I]),

@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <stdarg.h>
 
+#include <atomic>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -23,23 +24,26 @@ void linr_set_error(const char *fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+// SM count of the CURRENT device (cached per device: ranks of one process may drive different GPUs)
 int linr_sm_count() {
-    static int sm = 0;
-    if (!sm) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm <= 0)
-            sm = 148;
+    static std::atomic<int> sm[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int v = sm[dev].load(std::memory_order_relaxed);
+    if (!v) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        sm[dev].store(v, std::memory_order_relaxed);
     }
-    return sm;
+    return v;
 }
 
 // ---------------------------------------------------------------------------------------------- profiler
 namespace linr {
 namespace {
 struct ProfState {
-    uint32_t mask = 0;
-    int64_t launches[K_NCLASS] = {0};
-    int64_t units[K_NCLASS] = {0};
+    std::atomic<uint32_t> mask{0};
+    std::atomic<int64_t> launches[K_NCLASS];
+    std::atomic<int64_t> units[K_NCLASS];
     std::vector<cudaEvent_t> ev[K_NCLASS];  // begin/end pairs recorded so far
     std::vector<cudaEvent_t> pool;          // recycled events
     double ms_done[K_NCLASS] = {0};
@@ -70,19 +74,21 @@ void prof_drain(int c) {
     v.clear();
 }
 }  // namespace
+// Launch counters are relaxed atomics: with timing off (mask 0, the normal state) a launch takes no lock.
 void prof_begin(int cls, int64_t units, cudaStream_t s) {
-    std::lock_guard<std::mutex> lock(g_prof.mu);
-    g_prof.launches[cls] += 1;
-    g_prof.units[cls] += units;
-    if (g_prof.mask >> cls & 1u) {
+    g_prof.launches[cls].fetch_add(1, std::memory_order_relaxed);
+    g_prof.units[cls].fetch_add(units, std::memory_order_relaxed);
+    if (g_prof.mask.load(std::memory_order_relaxed) >> cls & 1u) {
+        std::lock_guard<std::mutex> lock(g_prof.mu);
         cudaEvent_t e = prof_event();
         cudaEventRecord(e, s);
         g_prof.ev[cls].push_back(e);
     }
 }
 void prof_end(int cls, cudaStream_t s) {
-    std::lock_guard<std::mutex> lock(g_prof.mu);
-    if (g_prof.mask >> cls & 1u) {
+    if (g_prof.mask.load(std::memory_order_relaxed) >> cls & 1u) {
+        std::lock_guard<std::mutex> lock(g_prof.mu);
+        if (g_prof.ev[cls].size() % 2 == 0) return;   // timing was switched on between begin and end: no open pair
         cudaEvent_t e = prof_event();
         cudaEventRecord(e, s);
         g_prof.ev[cls].push_back(e);
@@ -268,33 +274,73 @@ RowMap map_of(const linr_rows *r) {
                   st ? r->d_pair_list : nullptr};
 }
 
-// ---- weight bank (constant memory is one per process: a single stream owns it, everybody else uses shared memory)
-struct BankOwner {
+// ---- contexts and the weight bank.  The constant bank exists once per device, so ONE context per device holds it at a
+// time, for the duration of a training call (linr_net_forward(train) / linr_net_backward): the call claims the bank,
+// stages its fills, launches, and at its end records an event on its stream and lets go.  The next claimant -- the same
+// or another context, on the same or another stream -- first makes its stream wait for that event, so a fill never
+// overwrites weights that launches in flight still read.  A call that finds the bank busy (another host thread is in
+// the middle of a training call) runs the shared-memory kernel variant instead, as every coding forward (train = 0)
+// does: it executes the same FMAs in the same order, so the outputs are bit-identical.  Calls made without a current
+// context use the device's default context.
+}  // namespace
+struct linr_ctx {
+    int device = 0;
+    bool is_default = false;
+    cudaEvent_t done = nullptr;               // end of this context's last training call (created on first use)
+    std::atomic<int64_t> bank_launches{0};    // constant-bank (CW) conv launches made through this context
+    std::atomic<int64_t> bank_calls{0};       // training calls that held the bank
+};
+namespace {
+struct BankState {
     std::mutex mu;
-    bool owned = false;
-    cudaStream_t stream = nullptr;
-    int device = -1;
-    std::thread::id thread;   // fills and launches of two host threads would interleave even on one stream
-} g_bank_owner;
+    linr_ctx *holder = nullptr;   // context inside a training call right now
+    linr_ctx *last = nullptr;     // context whose `done` event guards the bank's current contents
+} g_bank[64];
+linr_ctx g_default_ctx[64];
+thread_local linr_ctx *t_ctx = nullptr;
+
+linr_ctx *current_ctx() {
+    if (t_ctx) return t_ctx;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    g_default_ctx[dev].device = dev, g_default_ctx[dev].is_default = true;
+    return &g_default_ctx[dev];
+}
 
 bool bank_claim(cudaStream_t s) {
     static const bool disabled = getenv("LINR_NO_WEIGHT_BANK") != nullptr;
     if (disabled) return false;
+    linr_ctx *me = current_ctx();
     int dev = 0;
-    cudaGetDevice(&dev);
-    std::lock_guard<std::mutex> lock(g_bank_owner.mu);
-    if (!g_bank_owner.owned) {
-        g_bank_owner.owned = true, g_bank_owner.stream = s, g_bank_owner.device = dev;
-        g_bank_owner.thread = std::this_thread::get_id();
-        return true;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || dev != me->device) return false;
+    BankState &b = g_bank[dev];
+    std::lock_guard<std::mutex> lock(b.mu);
+    if (b.holder != nullptr) return false;                                   // busy: another host thread is mid-call
+    if (!me->done && cudaEventCreateWithFlags(&me->done, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        me->done = nullptr;
+        return false;
     }
-    return g_bank_owner.stream == s && g_bank_owner.device == dev && g_bank_owner.thread == std::this_thread::get_id();
+    if (b.last && b.last->done) cudaStreamWaitEvent(s, b.last->done, 0);     // the previous user's launches retire first
+    b.holder = me;
+    me->bank_calls.fetch_add(1, std::memory_order_relaxed);
+    return true;
+}
+void bank_release(cudaStream_t s) {
+    linr_ctx *me = current_ctx();
+    BankState &b = g_bank[me->device];
+    std::lock_guard<std::mutex> lock(b.mu);
+    if (b.holder != me) return;
+    cudaEventRecord(me->done, s);
+    b.last = me;
+    b.holder = nullptr;
 }
 
-struct BankCtx {   // lives for one linr_net_forward(train) / linr_net_backward call on the owning stream
+struct BankCtx {   // lives for one linr_net_forward(train) / linr_net_backward call that holds the bank
     const Layout *L;
     float *stage;
     int cur_fill;
+    cudaStream_t stream;
 };
 thread_local BankCtx *t_bank = nullptr;
 
@@ -310,12 +356,15 @@ bool bank_begin(BankCtx &ctx, const Layout &L, const float *params, float *stage
         if (it.fill >= f0 && it.fill < f1 && items.n < BANK_MAX_ITEMS) items.it[items.n++] = it;
     ProfScope prof(K_REDUCE, items.n, s);
     bank_stage_kernel<<<items.n, 256, 0, s>>>(params, items, stage);
-    ctx.L = &L, ctx.stage = stage, ctx.cur_fill = -1;
+    ctx.L = &L, ctx.stage = stage, ctx.cur_fill = -1, ctx.stream = s;
     t_bank = &ctx;
     return true;
 }
 struct BankScope {
-    ~BankScope() { t_bank = nullptr; }
+    ~BankScope() {
+        if (t_bank) bank_release(t_bank->stream);
+        t_bank = nullptr;
+    }
 };
 
 // dynamic shared memory above 48 KB has to be opted into once per function and device (`done`: the caller's flags
@@ -361,6 +410,7 @@ int launch_conv(const ConvArgs &a, int G, cudaStream_t s) {
             }
             dim3 grid((unsigned)ceil_div64(a.map.n_rows, (ConvCfg<CIN, COUT, MODE, true>::ROWS)), (unsigned)G);
             ProfScope prof(cls, a.map.n_rows * G, s);
+            current_ctx()->bank_launches.fetch_add(1, std::memory_order_relaxed);
             conv27_kernel<CIN, COUT, MODE, true><<<grid, CONV_TPB, 0, s>>>(b);
             return (int)grid.x;
         }
@@ -783,13 +833,54 @@ int linr_device_info(int device, int *sm_count, int64_t *l2_bytes) {
     return LINR_OK;
 }
 
+int linr_ctx_create(int device, linr_ctx **out) {
+    LINR_REQUIRE(out != nullptr, "linr_ctx_create: null output");
+    int n = 0;
+    LINR_CHECK_CUDA(cudaGetDeviceCount(&n));
+    LINR_REQUIRE(device >= 0 && device < n && device < 64, "linr_ctx_create: device %d out of range", device);
+    linr_ctx *c = new linr_ctx();
+    c->device = device;
+    *out = c;
+    return LINR_OK;
+}
+int linr_ctx_destroy(linr_ctx *ctx) {
+    if (!ctx) return LINR_OK;
+    LINR_REQUIRE(!ctx->is_default, "linr_ctx_destroy: not a context made by linr_ctx_create");
+    if (t_ctx == ctx) t_ctx = nullptr;
+    {
+        BankState &b = g_bank[ctx->device];
+        std::lock_guard<std::mutex> lock(b.mu);
+        LINR_REQUIRE(b.holder != ctx, "linr_ctx_destroy: the context is inside a training call");
+        if (b.last == ctx) {
+            // its launches may still read the bank: wait for them, then nobody guards the bank's contents
+            if (ctx->done) cudaEventSynchronize(ctx->done);
+            b.last = nullptr;
+        }
+    }
+    if (ctx->done) cudaEventDestroy(ctx->done);
+    delete ctx;
+    return LINR_OK;
+}
+int linr_ctx_set_current(linr_ctx *ctx) {
+    t_ctx = ctx;
+    return LINR_OK;
+}
+int64_t linr_ctx_bank_calls(const linr_ctx *ctx) {
+    const linr_ctx *c = ctx ? ctx : current_ctx();
+    return c->bank_calls.load(std::memory_order_relaxed);
+}
+int64_t linr_ctx_bank_launches(const linr_ctx *ctx) {
+    const linr_ctx *c = ctx ? ctx : current_ctx();
+    return c->bank_launches.load(std::memory_order_relaxed);
+}
+
 int linr_prof_enable(uint32_t class_mask) {
     std::lock_guard<std::mutex> lock(g_prof.mu);
     for (int c = 0; c < K_NCLASS; ++c) {
         prof_drain(c);
-        g_prof.launches[c] = 0, g_prof.units[c] = 0, g_prof.ms_done[c] = 0.0;
+        g_prof.launches[c].store(0), g_prof.units[c].store(0), g_prof.ms_done[c] = 0.0;
     }
-    g_prof.mask = class_mask;
+    g_prof.mask.store(class_mask);
     return LINR_OK;
 }
 int linr_prof_read(int cls, double *ms_total, int64_t *launches, int64_t *units) {
@@ -797,8 +888,8 @@ int linr_prof_read(int cls, double *ms_total, int64_t *launches, int64_t *units)
     std::lock_guard<std::mutex> lock(g_prof.mu);
     prof_drain(cls);
     if (ms_total) *ms_total = g_prof.ms_done[cls];
-    if (launches) *launches = g_prof.launches[cls];
-    if (units) *units = g_prof.units[cls];
+    if (launches) *launches = g_prof.launches[cls].load();
+    if (units) *units = g_prof.units[cls].load();
     return LINR_OK;
 }
 int linr_prof_classes(void) { return K_NCLASS; }
@@ -1011,7 +1102,16 @@ int linr_param_quant(const float *d_params, int64_t n, int bitdepth, uint8_t *d_
     LINR_REQUIRE(bitdepth >= 1 && bitdepth <= 8, "bitdepth must be in [1,8]");
     LINR_REQUIRE(n > 0, "empty parameter vector");
     ProfScope prof(K_ADAM, n, (cudaStream_t)stream);
-    quant_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_params, n, (float)((1 << bitdepth) - 1), d_q, d_recon, d_stats);
+    quant_kernel<uint8_t><<<1, 1024, 0, (cudaStream_t)stream>>>(d_params, n, (float)((1 << bitdepth) - 1), d_q, d_recon, d_stats);
+    LINR_LAUNCH_CHECK();
+    return LINR_OK;
+}
+
+int linr_param_quant16(const float *d_params, int64_t n, int bitdepth, uint16_t *d_q, float *d_recon, float *d_stats, void *stream) {
+    LINR_REQUIRE(bitdepth >= 1 && bitdepth <= 16, "bitdepth must be in [1,16]");
+    LINR_REQUIRE(n > 0, "empty parameter vector");
+    ProfScope prof(K_ADAM, n, (cudaStream_t)stream);
+    quant_kernel<uint16_t><<<1, 1024, 0, (cudaStream_t)stream>>>(d_params, n, (float)((1 << bitdepth) - 1), d_q, d_recon, d_stats);
     LINR_LAUNCH_CHECK();
     return LINR_OK;
 }

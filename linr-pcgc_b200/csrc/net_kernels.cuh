@@ -1387,7 +1387,8 @@ __global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, 
 }
 
 // One block: min/max -> quantise -> mean -> mean abs dev -> dequantise (model_size_est.py:72-91,410-411).
-__global__ void __launch_bounds__(1024) quant_kernel(const float *__restrict__ p, int64_t n, float smax, uint8_t *__restrict__ q,
+template <typename QT>   // uint8_t symbols for bit depths <= 8, uint16_t for 9..16
+__global__ void __launch_bounds__(1024) quant_kernel(const float *__restrict__ p, int64_t n, float smax, QT *__restrict__ q,
                                                      float *__restrict__ recon, float *__restrict__ stats) {
     __shared__ float s_a[1024], s_b[1024];
     __shared__ double s_d[1024];
@@ -1411,7 +1412,7 @@ __global__ void __launch_bounds__(1024) quant_kernel(const float *__restrict__ p
     for (int64_t i = threadIdx.x; i < n; i += 1024) {
         // round((w - min) / range * smax): same op order as torch (division, then multiply), half-to-even
         const float s = rintf(__fmul_rn(__fdiv_rn(__fsub_rn(p[i], mn), rng), smax));
-        q[i] = (uint8_t)s;
+        q[i] = (QT)s;
         recon[i] = __fadd_rn(__fmul_rn(__fdiv_rn(s, smax), rng), mn);
         sum += (double)s;
     }

@@ -37,6 +37,33 @@ class NetRunner:
         self.ws = None
         self.reserve(max_rows)
         self.bits = torch.zeros(1, dtype=torch.float64, device=self.device)
+        # a training runner is one user of the device: its context takes turns at the constant weight bank
+        # (linr_ctx_create / include/linr_b200.h)
+        self.ctx = None
+        if train:
+            idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            h = C.c_void_p()
+            check(self.lib.linr_ctx_create(int(idx), C.byref(h)), "linr_ctx_create")
+            self.ctx = h
+
+    def close(self):
+        """Destroy the context (waits for its last training call if the bank still holds its weights)."""
+        if getattr(self, "ctx", None) is not None:
+            self.lib.linr_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def bank_calls(self) -> int:
+        """Training calls of this runner that ran on the constant-bank kernels."""
+        return int(self.lib.linr_ctx_bank_calls(self.ctx)) if self.ctx is not None else 0
+
+    def bank_launches(self) -> int:
+        return int(self.lib.linr_ctx_bank_launches(self.ctx)) if self.ctx is not None else 0
 
     def reserve(self, rows: int):
         if rows <= self.max_rows and self.ws is not None:
@@ -57,6 +84,8 @@ class NetRunner:
         n = t.n_rows
         self.reserve(n)
         rows = t.rows()
+        if train:
+            self.lib.linr_ctx_set_current(self.ctx)
         check(self.lib.linr_net_forward_stages(ptr(params), self.S, C.byref(rows), int(stages[0]), int(stages[1]),
                                                1 if train else 0, loss_scale,
                                                ptr(self.probs) if want_probs else None, ptr(self.cdf) if want_cdf else None,
@@ -74,6 +103,7 @@ class NetRunner:
     def backward(self, params: torch.Tensor, t: RowTables, grad: torch.Tensor, stages=(0, 8)):
         assert grad.is_cuda and grad.numel() >= self.P
         rows = t.rows()
+        self.lib.linr_ctx_set_current(self.ctx)
         check(self.lib.linr_net_backward_stages(ptr(params), self.S, C.byref(rows), int(stages[0]), int(stages[1]), ptr(grad),
                                                 ptr(self.ws), self.ws.numel(), stream_ptr()), "linr_net_backward_stages")
 
@@ -119,11 +149,16 @@ def adam_step(params, grad, m, v, step: int, lr: float, b1=0.9, b2=0.999, eps=1e
 
 def param_quant(params: torch.Tensor, bitdepth: int = 8):
     """quant_uniform2 + Laplace stats (model_size_est.py:72-91,410-411) -> (q u8, recon f32, stats[min,max,mu,b])."""
-    q = torch.empty(params.numel(), dtype=torch.uint8, device=params.device)
     recon = torch.empty_like(params)
     stats = torch.empty(4, dtype=torch.float32, device=params.device)
-    check(_lib.load().linr_param_quant(ptr(params), params.numel(), bitdepth, ptr(q), ptr(recon), ptr(stats), stream_ptr()),
-          "linr_param_quant")
+    if bitdepth <= 8:
+        q = torch.empty(params.numel(), dtype=torch.uint8, device=params.device)
+        check(_lib.load().linr_param_quant(ptr(params), params.numel(), bitdepth, ptr(q), ptr(recon), ptr(stats), stream_ptr()),
+              "linr_param_quant")
+    else:      # 9..16 bit symbols (int16 storage, read as uint16)
+        q = torch.empty(params.numel(), dtype=torch.int16, device=params.device)
+        check(_lib.load().linr_param_quant16(ptr(params), params.numel(), bitdepth, ptr(q), ptr(recon), ptr(stats), stream_ptr()),
+              "linr_param_quant16")
     return q, recon, stats
 
 

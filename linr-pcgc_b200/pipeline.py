@@ -58,19 +58,29 @@ def prepare_gop(points: Sequence[torch.Tensor], scale_num: Optional[int] = None,
     return frames
 
 
+def _side_info(comp: Dict, bitdepth: int) -> Dict:
+    """side_info.json (encoder.py:114); `cdf_version` only appears when it is not the reference's (so version-1 GOPs
+    stay byte-compatible with the reference's decoder)."""
+    side = dict(mu=comp["mu"], b=comp["b"], min_param=comp["min_param"], max_param=comp["max_param"],
+                enc_mode=comp["enc_mode"], bitdepth=bitdepth)
+    if int(comp.get("cdf_version", 1)) != model_compression.CDF_REFERENCE:
+        side["cdf_version"] = int(comp["cdf_version"])
+    return side
+
+
 def encode_gop(frames: Sequence[Frame], flat_params: torch.Tensor, scale_num: int, bitdepth: int = 8,
-               runner: Optional[NetRunner] = None, threads: Optional[int] = None) -> EncodedGop:
+               runner: Optional[NetRunner] = None, threads: Optional[int] = None,
+               cdf_version: int = model_compression.CDF_REFERENCE) -> EncodedGop:
     """Quantise the model, then code every frame with the *dequantised* parameters (encoder.py:101-103)."""
-    comp = model_compression.compress_model(flat_params, bitdepth)
+    comp = model_compression.compress_model(flat_params, bitdepth, cdf_version)
     recon = comp["recon_ret"]
     if runner is None:
         runner = NetRunner(scale_num, max(f.tables.n_rows for f in frames), flat_params.device, train=False)
     frame_bytes = codec.encode_frames(runner, recon, frames, threads)
     lows = [f.scale_coords(f.n_scales - 1).cpu().numpy() for f in frames]
     low = codec.pack_low_xyz(lows, [f.coord_min for f in frames])
-    side = dict(mu=comp["mu"], b=comp["b"], min_param=comp["min_param"], max_param=comp["max_param"],
-                enc_mode=comp["enc_mode"], bitdepth=bitdepth)
-    return EncodedGop(scale_num, side, comp["final_bytes"], comp["bit_real"], low, frame_bytes, [f.point_num for f in frames])
+    return EncodedGop(scale_num, _side_info(comp, bitdepth), comp["final_bytes"], comp["bit_real"], low, frame_bytes,
+                      [f.point_num for f in frames])
 
 
 def encode_gop_shared(frames: Sequence[Frame], flat_params: torch.Tensor, scale_num: int, bitdepth: int = 8,
@@ -97,9 +107,8 @@ def encode_gop_shared(frames: Sequence[Frame], flat_params: torch.Tensor, scale_
             frame_bytes[i] = fb
     lows = [f.scale_coords(f.n_scales - 1).cpu().numpy() for f in frames]
     low = codec.pack_low_xyz(lows, [f.coord_min for f in frames])
-    side = dict(mu=comp["mu"], b=comp["b"], min_param=comp["min_param"], max_param=comp["max_param"],
-                enc_mode=comp["enc_mode"], bitdepth=bitdepth)
-    return EncodedGop(scale_num, side, comp["final_bytes"], comp["bit_real"], low, frame_bytes, [f.point_num for f in frames])
+    return EncodedGop(scale_num, _side_info(comp, bitdepth), comp["final_bytes"], comp["bit_real"], low, frame_bytes,
+                      [f.point_num for f in frames])
 
 
 def decode_gop(enc: EncodedGop, device="cuda", workers: Optional[int] = None) -> List[torch.Tensor]:

@@ -59,6 +59,7 @@ class _TableCache:
             self.d.move_to_end(key)
             return hit[0]
         xyz = coords[:, -3:].to(torch.int32).contiguous()
+        _check_coordinate_set(coords, xyz)
         scale = torch.zeros(int(xyz.shape[0]), dtype=torch.uint8, device=xyz.device)
         tab = build_tables(xyz, scale)
         self.d[key] = (tab, coords)                 # keeps the key tensor (and, through `_linr_keep`, the un-batched
@@ -66,6 +67,27 @@ class _TableCache:
         if len(self.d) > self.cap:
             self.d.popitem(last=False)
         return tab
+
+
+def _check_coordinate_set(coords: torch.Tensor, xyz: torch.Tensor) -> None:
+    """The compact kernel map (9 anchors + 27 bits per row) and the hash insert assume ONE batch of x-major sorted,
+    unique rows -- the reference's invariant for every set it convolves (datautils/custom_dataset.py:308,
+    models/sort_functions.py:95-103).  Checked once per coordinate set (the tables are cached); anything else would
+    gather wrong rows silently, so it raises."""
+    n = int(xyz.shape[0])
+    if n == 0:
+        return
+    if coords.shape[1] == 4 and bool((coords[:, 0] != coords[0, 0]).any()):
+        raise NotImplementedError("linr_b200 MinkowskiEngine shim: one batch index per coordinate set (LINR-PCGC collates single frames)")
+    if int(xyz.min()) < 0 or int(xyz.max()) >= (1 << 20):
+        raise ValueError("linr_b200 MinkowskiEngine shim: coordinates must be in [0, 2^20)")
+    if n > 1:
+        k = (xyz[:, 0].to(torch.int64) << 40) | (xyz[:, 1].to(torch.int64) << 20) | xyz[:, 2].to(torch.int64)
+        d = k[1:] - k[:-1]
+        if bool((d <= 0).any()):
+            what = "duplicate rows" if bool((d == 0).any()) and not bool((d < 0).any()) else "rows that are not x-major sorted"
+            raise ValueError(f"linr_b200 MinkowskiEngine shim: coordinate set with {what}; sort it first "
+                             "(models/sort_functions.py sort_sparse_tensor) -- the kernel map needs sorted unique rows")
 
 
 _tables = _TableCache()
@@ -158,19 +180,13 @@ class SparseTensor:
         if other.coordinate_map_key == self.coordinate_map_key:
             return self._like(self.F + other.F)
         a, b = self.C, other.C
-        # union map: self's rows first (in order), then the rows only `other` has
+        # union map in x-major sorted order (torch.unique sorts rows lexicographically, batch column first): a union of
+        # sorted sets stays a valid input of the 27-offset convolution; equal sets keep their row order
         both = torch.cat([a, b], dim=0)
-        uniq, inv = torch.unique(both, dim=0, return_inverse=True)
-        first = torch.full((uniq.shape[0],), both.shape[0], dtype=torch.long, device=both.device)
-        first.scatter_reduce_(0, inv, torch.arange(both.shape[0], device=both.device), reduce="amin")
-        order = torch.argsort(first)                              # union rows in first-appearance order
-        rank = torch.empty_like(order)
-        rank[order] = torch.arange(order.numel(), device=order.device)
-        rows = rank[inv]
-        coords = both[first[order]]
+        coords, inv = torch.unique(both, dim=0, return_inverse=True)
         feats = torch.zeros((coords.shape[0], self.F.shape[1]), dtype=self.F.dtype, device=self.F.device)
-        feats.index_add_(0, rows[: a.shape[0]], self.F)
-        feats.index_add_(0, rows[a.shape[0]:], other.F)
+        feats.index_add_(0, inv[: a.shape[0]], self.F)
+        feats.index_add_(0, inv[a.shape[0]:], other.F)
         return SparseTensor(feats, coordinates=coords, coordinate_manager=self.coordinate_manager,
                             tensor_stride=self.tensor_stride)
 

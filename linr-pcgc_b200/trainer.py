@@ -38,6 +38,28 @@ class OptimState:
         return OptimState(self.params.clone(), self.m.clone(), self.v.clone(), self.step, self.sched_step, self.lr)
 
 
+def sched_after_step(st: OptimState, step_size: int, gamma: float) -> None:
+    """torch.optim.lr_scheduler.StepLR.step() after an optimiser step (main.py:252,321): the chainable form multiplies the
+    CURRENT lr by gamma every `step_size` calls -- it does not recompute it from the initial lr, so the per-epoch floor
+    below and a warm start from another GOP's lr carry over."""
+    st.sched_step += 1
+    if st.sched_step % step_size == 0:
+        st.lr *= gamma
+
+
+def sched_end_epoch(st: OptimState, min_lr: float) -> None:
+    """main.py:433-437: after every epoch the lr is raised back to `min_lr` if it fell below."""
+    if st.lr < min_lr:
+        st.lr = min_lr
+
+
+def sched_new_gop(st: OptimState) -> OptimState:
+    """A later GOP loads GOP 0's optimizer state dict (lr, Adam moments and step counts continue, main.py:241-246) and
+    builds a FRESH StepLR (main.py:252): the decay counter restarts at 0."""
+    st.sched_step = 0
+    return st
+
+
 class GopTrainer:
     def __init__(self, scale_num: int, device="cuda", learning_rate: float = 0.01, gamma: float = 0.992,
                  step_size: int = 32, min_lr: float = 4e-4, decay_rate: float = 1e-4, seed: Optional[int] = None,
@@ -51,7 +73,7 @@ class GopTrainer:
             flat = P.init_flat(scale_num, seed).to(self.device)
             state = OptimState(flat, torch.zeros(n, device=self.device), torch.zeros(n, device=self.device), 0, 0, learning_rate)
         else:
-            state.sched_step = 0   # a fresh StepLR per GOP (main.py:252): lr and Adam state continue, the decay phase restarts
+            sched_new_gop(state)
         self.state = state
         self.grad = torch.empty(n, dtype=torch.float32, device=self.device)
         self.runner = NetRunner(scale_num, max_rows, self.device, train=True)
@@ -61,6 +83,10 @@ class GopTrainer:
         self.split = self.stages != (0, 8)
         self.bits_log: List[torch.Tensor] = []
 
+    def close(self):
+        """Destroy the runner's context (NetRunner.close); the trainer cannot step afterwards."""
+        self.runner.close()
+
     def reset(self, state: Optional[OptimState] = None, seed: Optional[int] = None, learning_rate: float = 0.01):
         """Start another GOP with this trainer's workspace: from `state` (a later GOP, seeded by GOP 0: main.py:102-104)
         or from a fresh random model."""
@@ -68,7 +94,7 @@ class GopTrainer:
             flat = P.init_flat(self.S, seed).to(self.device)
             state = OptimState(flat, torch.zeros_like(flat), torch.zeros_like(flat), 0, 0, learning_rate)
         else:
-            state.sched_step = 0
+            sched_new_gop(state)
         self.state = state
 
     # one frame-iteration (main.py:305-321)
@@ -84,14 +110,11 @@ class GopTrainer:
             self.grad_hook(self.grad)
         st.step += 1
         adam_step(st.params, self.grad, st.m, st.v, st.step, st.lr, wd=self.wd)
-        st.sched_step += 1
-        if st.sched_step % self.step_size == 0:
-            st.lr *= self.gamma
+        sched_after_step(st, self.step_size, self.gamma)
         return out.get("bits")
 
     def end_epoch(self):
-        if self.state.lr < self.min_lr:
-            self.state.lr = self.min_lr
+        sched_end_epoch(self.state, self.min_lr)
 
     def fit(self, frames: Sequence[Frame], epochs: int, log: Optional[Callable[[Dict], None]] = None) -> List[float]:
         """`epochs` passes over the GOP; returns the mean loss (bits/point) per epoch (one host sync per epoch)."""

@@ -181,6 +181,11 @@ def checkpoint_fixture():
 
 
 if __name__ == "__main__":
+    if sys.argv[1:] == ["net_mid"]:
+        # ~40k points, 9 bit: 5 scales, ~14k parent rows -> several 256-row chunks of partial sums per kernel (the tiny
+        # fixture fits in one), every scale's SCE MLP exercised
+        net_fixture("mid", synth.make_sequence("tiny", 1, bits=9, target=40_000)[0].numpy(), seed=2)
+        sys.exit(0)
     sort_fixture()
     tiny = synth.make_sequence("tiny", 1)[0].numpy()
     int_fixture("tiny", tiny + np.array([3, -2, 7], np.int32))     # non-zero / negative min exercised
@@ -190,4 +195,5 @@ if __name__ == "__main__":
     mid = synth.make_sequence("tiny", 1, bits=8, target=12_000)[0].numpy()
     int_fixture("mid", mid)
     net_fixture("tiny", tiny, seed=1)
+    net_fixture("mid", synth.make_sequence("tiny", 1, bits=9, target=40_000)[0].numpy(), seed=2)
     checkpoint_fixture()

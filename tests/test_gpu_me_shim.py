@@ -154,19 +154,42 @@ def test_merge_prune_cat_union(env):
     sub_nbr = torch.from_numpy(O.nbr27(coord[mask.cpu().numpy()]).astype(np.int64))
     ref = O.conv27(f1[mask].cpu(), sub_nbr, conv.kernel.detach().cpu(), None)
     np.testing.assert_allclose(conv(sub).F.detach().cpu().numpy(), ref.numpy(), **TOL)
-    # union of two different sets on one manager: rows of the left operand first
+    # union of two different sets on one manager: x-major sorted whatever the operand order, so it can be convolved
     a = ME.SparseTensor(f1[: n // 2], coordinates=s1.C[: n // 2], device="cuda")
     b = ME.SparseTensor(f1[n // 4:], coordinates=s1.C[n // 4:], coordinate_manager=a.coordinate_manager, device="cuda")
-    u = a + b
-    assert torch.equal(u.C, s1.C)
     want = torch.zeros_like(f1)
     want[: n // 2] += f1[: n // 2]
     want[n // 4:] += f1[n // 4:]
-    assert torch.allclose(u.F, want)
+    for u in (a + b, b + a):
+        assert torch.equal(u.C, s1.C)
+        assert torch.allclose(u.F, want)
+    ref_u = O.conv27(want.cpu(), nbr, conv.kernel.detach().cpu(), None)
+    np.testing.assert_allclose(conv(b + a).F.detach().cpu().numpy(), ref_u.numpy(), **TOL)
     with pytest.raises(ValueError):
         s1 + s2                                                           # different managers
     with pytest.raises(ValueError):
         ME.cat(s1, s2)
+
+
+def test_coordinate_sets_are_validated(env):
+    """The compact kernel map needs ONE batch of x-major sorted unique rows: anything else raises instead of gathering
+    wrong rows (the check runs once per coordinate set, when its tables are built)."""
+    ME, _, O, coord, nbr = env
+    conv = ME.MinkowskiConvolution(8, 8, kernel_size=3, stride=1, bias=False, dimension=3).cuda()
+    n = len(coord)
+    x = torch.randn(n, 8).cuda()
+    perm = torch.randperm(n)
+    C0 = torch.cat([torch.zeros((n, 1), dtype=torch.int32), torch.from_numpy(coord)], dim=1).cuda()
+    with pytest.raises(ValueError, match="sorted"):
+        conv(ME.SparseTensor(x, coordinates=C0[perm.cuda()].contiguous()))
+    dup = torch.cat([C0[:5], C0[4:]], dim=0)
+    with pytest.raises(ValueError, match="duplicate"):
+        conv(ME.SparseTensor(torch.randn(n + 1, 8).cuda(), coordinates=dup.contiguous()))
+    two = C0.clone()
+    two[n // 2:, 0] = 1
+    with pytest.raises(NotImplementedError, match="batch"):
+        conv(ME.SparseTensor(x, coordinates=two))
+    conv(ME.SparseTensor(x, coordinates=C0))       # the sorted unique single-batch set is accepted
 
 
 def test_kernel_map_cache_follows_the_coordinate_tensor(env):

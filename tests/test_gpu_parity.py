@@ -204,8 +204,11 @@ def test_full_size_octree_round_trip(L, shape, bits):
 
 
 # ------------------------------------------------------------------------------------------------ network
-def _net_case(L, O):
-    g = _load("net_tiny.npz")
+NET_FIXTURES = ["tiny", "mid"]   # mid: ~40k points, 5 scales, ~14k rows -> several 256-row chunks of partial sums per kernel
+
+
+def _net_case(L, O, name="tiny"):
+    g = _load(f"net_{name}.npz")
     S = int(g["scale_num"])
     sd = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w:")}
     flat = O.flatten_params(sd, S).contiguous()
@@ -226,8 +229,9 @@ def test_param_layout_matches_checkpoint_contract(L, O):
     assert L.net.param_count(7) == 54712
 
 
-def test_forward_probs_bits_cdf(L, O):
-    g, S, sd, flat, fr = _net_case(L, O)
+@pytest.mark.parametrize("fixture", NET_FIXTURES)
+def test_forward_probs_bits_cdf(L, O, fixture):
+    g, S, sd, flat, fr = _net_case(L, O, fixture)
     run = L.net.NetRunner(S, fr.tables.n_rows, "cuda", train=False)
     out = run.forward(flat.cuda(), fr.tables, want_probs=True, want_cdf=True, want_bits=True)
     probs = out["probs"].cpu().numpy()
@@ -241,8 +245,9 @@ def test_forward_probs_bits_cdf(L, O):
     assert (cdf == O.cdf_u16_binary(probs.reshape(-1)).reshape(cdf.shape)).all()
 
 
-def test_backward_adam_match_and_deterministic(L, O):
-    g, S, sd, flat, fr = _net_case(L, O)
+@pytest.mark.parametrize("fixture", NET_FIXTURES)
+def test_backward_adam_match_and_deterministic(L, O, fixture):
+    g, S, sd, flat, fr = _net_case(L, O, fixture)
     P = flat.numel()
     run = L.net.NetRunner(S, fr.tables.n_rows, "cuda", train=True)
     params = flat.cuda()
@@ -272,14 +277,44 @@ def test_backward_adam_match_and_deterministic(L, O):
     np.testing.assert_allclose(p2.cpu().numpy(), g["flat_after_adam"], rtol=1e-5, atol=1e-6)
 
 
-def test_param_quant_bit_exact(L, O):
-    g, S, sd, flat, fr = _net_case(L, O)
+@pytest.mark.parametrize("fixture", NET_FIXTURES)
+def test_param_quant_bit_exact(L, O, fixture):
+    g, S, sd, flat, fr = _net_case(L, O, fixture)
     q, recon, stats = L.net.param_quant(flat.cuda(), 8)
     np.testing.assert_array_equal(recon.cpu().numpy(), g["q_recon"])
     st = stats.cpu().numpy()
     assert st[0] == g["q_min"] and st[1] == g["q_max"] and st[2] == g["q_mu"] and st[3] == g["q_b"]
     qo, _, _, _ = O.quant_uniform2(flat, 8)
     np.testing.assert_array_equal(q.cpu().numpy(), qo.numpy().astype(np.uint8))
+
+
+def test_model_coder_versions_and_bit_depths(L, O):
+    """(1) cdf_version 2 fixes the Laplace row quirk ([0,c1..cL] instead of [c1..cL,0],
+    model_size_est.py:473-478): same symbols, decodable, never larger; (2) model_bitdepth 9..16 -- which the reference
+    writes but cannot read back (model_size_est.py:546-548) -- round-trips through 16-bit symbols."""
+    from linr_pcgc_b200 import model_compression as MC
+    g, S, sd, flat, fr = _net_case(L, O, "mid")
+    params = flat.cuda()
+    n = params.numel()
+    sizes = {}
+    for ver in (MC.CDF_REFERENCE, MC.CDF_FIXED):
+        c = MC.compress_model(params, 8, ver)
+        assert c["enc_mode"] == 2 and c["cdf_version"] == ver
+        rec = MC.decompress_model(dict(c), n)
+        assert torch.equal(rec, c["recon_ret"])
+        sizes[ver] = len(c["final_bytes"])
+    assert sizes[MC.CDF_FIXED] <= sizes[MC.CDF_REFERENCE]
+    assert MC.compress_model(params, 8)["final_bytes"] == g["q_bytes"].tobytes()       # default = the reference's bitstream
+    rng = float(params.max() - params.min())
+    for bd in (9, 12, 16):
+        c = MC.compress_model(params, bd)
+        assert c["enc_mode"] in (0, 1) and c["bitdepth"] == bd
+        rec = MC.decompress_model(dict(c), n)
+        assert torch.equal(rec, c["recon_ret"])
+        assert float((rec - params).abs().max()) <= 0.51 * rng / (2 ** bd - 1) + 1e-6   # uniform quantiser: half a step (+ fp32 rounding)
+        q = (c["quant"].to(torch.int32) & 0xFFFF)
+        assert int(q.max()) == 2 ** bd - 1 and int(q.min()) == 0
+    print("model.bin bytes: reference row %d, fixed row %d (%.2f %% smaller)" % (sizes[1], sizes[2], 100 * (1 - sizes[2] / sizes[1])))
 
 
 def test_single_layer_conv_entry_points(L, O):
@@ -350,8 +385,9 @@ def test_full_size_conv_identities(L):
 
 
 # ------------------------------------------------------------------------------------------------ coding
-def test_encode_decode_lossless_and_bpp(L, O):
-    g, S, sd, flat, fr = _net_case(L, O)
+@pytest.mark.parametrize("fixture", NET_FIXTURES)
+def test_encode_decode_lossless_and_bpp(L, O, fixture):
+    g, S, sd, flat, fr = _net_case(L, O, fixture)
     params = flat.cuda()
     run = L.net.NetRunner(S, fr.tables.n_rows, "cuda", train=False)
     all_bytes = L.codec.encode_frame(run, params, fr)
@@ -403,6 +439,44 @@ def test_weight_bank_variant_is_bit_identical(L, O):
     tr_run.backward(params, fr.tables, grad1)
     torch.cuda.synchronize()
     assert torch.equal(pc, pa) and torch.equal(grad1, grad2)
+
+
+def test_contexts_take_turns_at_the_weight_bank(L, O):
+    """linr_ctx (include/linr_b200.h): a trainer on stream A, destroyed, then a trainer on stream B -- and two live
+    trainers stepping alternately -- all run their training calls on the constant-bank kernels (round 1: the first
+    (thread, stream) pair kept the bank for the life of the process and everybody else fell back silently)."""
+    g, S, sd, flat, fr = _net_case(L, O)
+    params = flat.cuda()
+    grads = []
+
+    def one_iteration(run):
+        run.forward(params, fr.tables, train=True, loss_scale=1.0 / fr.point_num)
+        grad = torch.empty_like(params)
+        run.backward(params, fr.tables, grad)
+        return grad
+
+    a = L.net.NetRunner(S, fr.tables.n_rows, "cuda", train=True)
+    grads.append(one_iteration(a))
+    assert a.bank_calls() == 2 and a.bank_launches() > 10           # forward + backward, every multi-group conv launch
+    a.close()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        b = L.net.NetRunner(S, fr.tables.n_rows, "cuda", train=True)
+        grads.append(one_iteration(b))
+        side.synchronize()
+        assert b.bank_calls() == 2 and b.bank_launches() > 10
+    c = L.net.NetRunner(S, fr.tables.n_rows, "cuda", train=True)    # two live trainers, one host thread: both get their turn
+    for _ in range(2):
+        with torch.cuda.stream(side):
+            grads.append(one_iteration(b))
+        grads.append(one_iteration(c))
+    torch.cuda.synchronize()
+    assert b.bank_calls() == 6 and c.bank_calls() == 4
+    assert all(torch.equal(grads[0], x) for x in grads[1:])          # same bits whoever held the bank, whatever the stream
+    inf = L.net.NetRunner(S, fr.tables.n_rows, "cuda", train=False)
+    assert inf.bank_calls() == 0 and inf.ctx is None                 # coding runners never touch the bank
+    b.close(), c.close()
 
 
 def test_two_trainers_in_two_host_threads_match_serial_runs(L, O):
@@ -522,6 +596,73 @@ def test_gop_overfit_tracks_oracle_training_and_bpp(L, O):
     got_bytes = sum(len(b) for f in frames for b in L.codec.encode_frame(run, tr.state.params, f))
     assert abs(got_bytes - ref_bytes) <= 0.005 * ref_bytes, (got_bytes, ref_bytes)
     np.testing.assert_allclose(tr.state.params.cpu().numpy(), flat.numpy(), rtol=0, atol=2e-3)
+
+
+def test_two_gops_track_torch_adam_steplr_oracle(L, O):
+    """GOP-level schedule semantics against the classes the reference itself uses: the CPU oracle is stepped by
+    torch.optim.Adam (L2 1e-4) + StepLR per frame with the per-epoch min_lr floor, and a second GOP loads the first one's
+    optimizer state dict and builds a fresh StepLR (main.py:231-252,319-321,433-437,102-104).  44 optimiser steps cross
+    eight StepLR boundaries, the floor, and a GOP boundary whose step count is not a multiple of step_size.  The CUDA
+    path (GopTrainer, seeded by OptimState) must use the same lr at every step and track the loss curve."""
+    import torch
+    from linr_pcgc_b200 import params as P
+    lr0, gamma, step_size, min_lr = 0.01, 0.7, 5, 4e-3
+    pts = L.synth.make_sequence("tiny", 8)
+    gops = [pts[:4], pts[4:]]
+    epochs = [6, 5]
+    S = L.frame.prepare_frame(pts[0].cuda(), None, 64).n_scales
+    flat0 = P.init_flat(S, seed=21)
+    # ---- oracle
+    w = torch.nn.Parameter(flat0.clone())
+    ref_losses, ref_lrs, sd = [], [], None
+    for gp, ep_n in zip(gops, epochs):
+        ofr = [O.prepare_frame(p.numpy(), S, 64) for p in gp]
+        nbrs = [[torch.from_numpy(O.nbr27(sc["coord"]).astype(np.int64)) for sc in f["scales"]] for f in ofr]
+        opt = torch.optim.Adam([w], lr=lr0, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+        if sd is not None:
+            opt.load_state_dict(sd)
+        sch = torch.optim.lr_scheduler.StepLR(opt, step_size=step_size, gamma=gamma)
+        for _ in range(ep_n):
+            acc = []
+            for f, nb in zip(ofr, nbrs):
+                opt.zero_grad()
+                bits = O.frame_bits(O.unflatten_params(w, S), f, nb)
+                (bits / f["point_num"]).backward()
+                ref_lrs.append(opt.param_groups[0]["lr"])
+                opt.step()
+                sch.step()
+                acc.append(float(bits.detach()) / f["point_num"])
+            for g in opt.param_groups:
+                if g["lr"] < min_lr:
+                    g["lr"] = min_lr
+            ref_losses.append(float(np.mean(acc)))
+        sd = opt.state_dict()
+    # ---- CUDA path
+    state = L.trainer.OptimState(flat0.clone().cuda(), torch.zeros_like(flat0).cuda(), torch.zeros_like(flat0).cuda(), 0, 0, lr0)
+    losses, lrs = [], []
+    for gp, ep_n in zip(gops, epochs):
+        frames = [L.frame.prepare_frame(p.cuda(), S, 64) for p in gp]
+        tr = L.trainer.GopTrainer(S, "cuda", lr0, gamma, step_size, min_lr, max_rows=max(f.tables.n_rows for f in frames), state=state)
+        for _ in range(ep_n):
+            # record the lr each step will use, then run the epoch
+            st = tr.state
+            probe = L.trainer.OptimState(st.params, st.m, st.v, st.step, st.sched_step, st.lr)
+            for _ in frames:
+                lrs.append(probe.lr)
+                L.trainer.sched_after_step(probe, step_size, gamma)
+            losses += tr.fit(frames, 1)
+        state = tr.state
+    assert len(ref_lrs) == 44 and len(set(np.round(ref_lrs, 12))) >= 5
+    np.testing.assert_allclose(lrs, ref_lrs, rtol=1e-12, atol=0)
+    assert tr.state.lr == pytest.approx(sd["param_groups"][0]["lr"], rel=1e-12) and tr.state.step == 44
+    np.testing.assert_allclose(losses, ref_losses, rtol=2e-3)
+    # parameters: Adam's m / sqrt(v) is scale-free, so the few entries whose gradient sits at rounding-noise level drift by
+    # up to lr per step between two fp32 implementations; compared in norm, with a bound on how many entries stray
+    got, want = tr.state.params.cpu().numpy(), w.detach().numpy()
+    assert np.linalg.norm(got - want) <= 2e-2 * np.linalg.norm(want)
+    assert (np.abs(got - want) > 5e-3).mean() < 5e-3
+    m_ref = sd["state"][0]["exp_avg"].numpy()
+    assert np.linalg.norm(tr.state.m.cpu().numpy() - m_ref) <= 5e-2 * np.linalg.norm(m_ref)
 
 
 def test_owlii_sized_iteration_and_codec(L, O):

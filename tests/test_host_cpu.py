@@ -175,6 +175,83 @@ def test_sharding_plans():
     assert sorted(sum([D.frame_share(32, 4, p) for p in range(4)], [])) == list(range(32))
 
 
+def test_lr_schedule_matches_torch_adam_steplr_across_gops():
+    """The host-side schedule against the classes the reference uses (torch.optim.Adam + StepLR stepped per frame,
+    main.py:231-252,319-321; min_lr floor per epoch, main.py:433-437; a later GOP loads the optimizer state and builds a
+    fresh StepLR, main.py:241-252).  Two StepLR boundaries, the floor, and a GOP boundary whose step count is NOT a
+    multiple of step_size are crossed; the lr used at every optimiser step must be equal."""
+    from linr_pcgc_b200.trainer import OptimState, sched_after_step, sched_end_epoch, sched_new_gop
+    lr0, gamma, step_size, min_lr, frames = 6e-4, 0.7, 5, 4e-4, 4
+
+    def torch_run(epochs_per_gop):
+        w = torch.nn.Parameter(torch.ones(3))
+        used, sd = [], None
+        for ep_n in epochs_per_gop:
+            opt = torch.optim.Adam([w], lr=lr0, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+            if sd is not None:
+                opt.load_state_dict(sd)
+            sch = torch.optim.lr_scheduler.StepLR(opt, step_size=step_size, gamma=gamma)
+            for _ in range(ep_n):
+                for _ in range(frames):
+                    opt.zero_grad()
+                    (w * w).sum().backward()
+                    used.append(opt.param_groups[0]["lr"])
+                    opt.step()
+                    sch.step()
+                for g in opt.param_groups:
+                    if g["lr"] < min_lr:
+                        g["lr"] = min_lr
+            sd = opt.state_dict()
+        return used
+
+    def ours(epochs_per_gop):
+        st = OptimState(torch.zeros(1), torch.zeros(1), torch.zeros(1), 0, 0, lr0)
+        used = []
+        for gi, ep_n in enumerate(epochs_per_gop):
+            if gi:
+                sched_new_gop(st)
+            for _ in range(ep_n):
+                for _ in range(frames):
+                    used.append(st.lr)
+                    st.step += 1
+                    sched_after_step(st, step_size, gamma)
+                sched_end_epoch(st, min_lr)
+        return used
+
+    want, got = torch_run([3, 3]), ours([3, 3])          # 12 steps per GOP: 12 % 5 != 0 -> the decay phase restarts in GOP 1
+    assert len(want) == 24 and len(set(want)) >= 4       # decays, the floor and the restart all show up
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)
+    assert min(want) >= min_lr * gamma and any(abs(x - min_lr) < 1e-15 for x in want)
+
+
+def test_gop_container_round_trips_and_matches_the_directory_layout(tmp_path):
+    """One-file container (container.py) <-> the reference's directory layout (encoder.py:84-146): same payload bytes,
+    ragged scale counts, both CDF versions of the side info."""
+    from linr_pcgc_b200 import container, pipeline
+    rng = np.random.default_rng(3)
+    fb = [[rng.bytes(int(rng.integers(1, 200))) for _ in range(ns)] for ns in (3, 3, 2, 1)]
+    for cdfv in (1, 2):
+        side = dict(mu=129.0, b=6.0, min_param=-0.75, max_param=0.5, enc_mode=2, bitdepth=8)
+        if cdfv != 1:
+            side["cdf_version"] = cdfv
+        enc = pipeline.EncodedGop(3, side, rng.bytes(777), 777 * 8 + 82.0, rng.bytes(99), fb, [1000, 1001, 1002, 17])
+        data = container.pack(enc)
+        back = container.unpack(data)
+        assert back == enc and back.side_info.get("cdf_version", 1) == cdfv
+        assert container.write(enc, str(tmp_path / f"g{cdfv}.linr")) == len(data) and container.read(str(tmp_path / f"g{cdfv}.linr")) == enc
+        # container -> directory -> container: nothing but the index changes
+        pipeline.write_gop(back, str(tmp_path / f"dir{cdfv}"))
+        again = pipeline.read_gop(str(tmp_path / f"dir{cdfv}"), 3, 4)
+        assert again.frame_bytes == fb and again.model_bytes == enc.model_bytes and again.low_enc_bytes == enc.low_enc_bytes
+        assert {k: again.side_info[k] for k in side} == side
+        overhead = len(data) - sum(len(b) for f in fb for b in f) - 777 - 99
+        assert overhead == container._HEAD.size + 4 * 6 + 16 * (2 + 9) == 268      # header + per-frame meta + index
+    with pytest.raises(ValueError):
+        container.unpack(b"garbage" * 20)
+    with pytest.raises(ValueError):
+        container.unpack(data[:-5])
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

@@ -77,8 +77,9 @@ def test_param_spec_matches_reference_model_and_checkpoint():
     assert abs(O.lr_at_step(7223) - ck["lr"]) / ck["lr"] < 0.01
 
 
-def test_network_forward_backward_adam_match_reference_flow():
-    g = _load("net_tiny.npz")
+@pytest.mark.parametrize("fixture", ["tiny", "mid"])
+def test_network_forward_backward_adam_match_reference_flow(fixture):
+    g = _load(f"net_{fixture}.npz")
     S = int(g["scale_num"])
     sd = _sd_from(g)
     fr = O.prepare_frame(g["points"], None, 64)
@@ -122,8 +123,9 @@ def test_codec_bitstreams_match_reference_flow():
     assert (dec2 == g["dec_coord"]).all()
 
 
-def test_model_compression_matches_reference():
-    g = _load("net_tiny.npz")
+@pytest.mark.parametrize("fixture", ["tiny", "mid"])
+def test_model_compression_matches_reference(fixture):
+    g = _load(f"net_{fixture}.npz")
     S = int(g["scale_num"])
     flat = O.flatten_params(_sd_from(g), S)
     c = O.compress_model(flat, 8)
