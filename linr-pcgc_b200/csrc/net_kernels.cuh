@@ -181,19 +181,124 @@ __device__ __forceinline__ void issue_ranges(const StagePlan &pl, const float *x
         if (pl.len[d] > 0) bulk_g2s(sx + (int64_t)pl.base[d] * ld, xg + (int64_t)pl.lo[d] * ld, (uint32_t)pl.len[d] * ld * 4u, bar);
 }
 
-template <int CIN, int COUT, int MODE, bool CW = false>
-__global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
-    constexpr int WMAX = CW ? 4 : ((MODE == 1) ? 27 * 7 * COUT : 27 * CIN * COUT);
-    constexpr int HQ = COUT / 2;  // accumulator pairs per row
-    constexpr int CONV_RPT = ConvCfg<CIN, COUT, MODE, CW>::RPT, CONV_ROWS = ConvCfg<CIN, COUT, MODE, CW>::ROWS;
-    __shared__ __align__(16) float s_w[WMAX];
-    __shared__ float s_b[COUT];
-    // head (MODE 2): W1 transposed [8][24] so that hidden-unit pairs are adjacent, then b1[24], w2[24], b2
-    __shared__ __align__(16) float s_head[(MODE == 2) ? (24 * 8 + 24 + 24 + 4) : 4];
-    __shared__ float s_red[CONV_TPB / 32];
-    __shared__ float s_pw[(MODE == 2) ? 1 : 36];   // fused pointwise weights [in][out] + bias
-    const int g = blockIdx.y;
-    const int cin = (MODE == 1) ? (a.cin_base + g * a.cin_step) : CIN;
+// Everything after the 27-offset accumulation of ONE output row `o` (bias, residual / accumulate, fused kernel_size-1
+// convs, ReLU / ReLU mask, store; MODE 2: MLP_k + sigmoid + CDF + bits + backward seed).  Shared by the lane = row
+// kernel and the pair-list kernel, so both produce the same bits.
+template <int CIN, int COUT, int MODE>
+__device__ __forceinline__ void conv_epilogue_row(const ConvArgs &a, int g, int64_t row, float (&o)[COUT], const float *s_b,
+                                                  const float *s_pw, const float *s_head, float &bits) {
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) o[co] += s_b[co];
+    if constexpr (MODE != 2) {
+        if (a.res.p) {
+            float t[COUT];
+            load_row<COUT>(tptr(a.res, g, row), t);
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) o[co] += t[co];
+        }
+        if (a.accum) {
+            float t[COUT];
+            load_row<COUT>(tptr(a.y, g, row), t);
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) o[co] += t[co];
+        }
+        if constexpr (COUT == 8) {
+            if (a.pw_mode == 3) {
+                float xv2[4], t[8];
+                load_row<4>(tptr(a.x2, g, row), xv2);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) t[i] = 0.f;
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+                    for (int co = 0; co < 8; ++co) t[co] = fmaf(xv2[ci], s_pw[ci * 8 + co], t[co]);
+#pragma unroll
+                for (int co = 0; co < 8; ++co) o[co] = t[co] + o[co];
+            }
+        }
+        if (a.relu) {
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) o[co] = fmaxf(o[co], 0.f);
+        }
+        if (a.rmask.p) {
+            float t[COUT];
+            load_row<COUT>(tptr(a.rmask, g, row), t);
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) o[co] = t[co] > 0.f ? o[co] : 0.f;
+        }
+        store_row<COUT>(tptr(a.y, g, row), o);
+        if (a.pw_mode == 1) {
+            float t[4];
+#pragma unroll
+            for (int co = 0; co < 4; ++co) t[co] = 0.f;
+#pragma unroll
+            for (int ci = 0; ci < COUT; ++ci)
+#pragma unroll
+                for (int co = 0; co < 4; ++co) t[co] = fmaf(o[ci], s_pw[ci * 4 + co], t[co]);
+#pragma unroll
+            for (int co = 0; co < 4; ++co) t[co] += s_pw[32 + co];
+            if (a.res2.p) {
+                float u[4];
+                load_row<4>(tptr(a.res2, g, row), u);
+#pragma unroll
+                for (int co = 0; co < 4; ++co) t[co] += u[co];
+            }
+            if (a.pw_relu) {
+#pragma unroll
+                for (int co = 0; co < 4; ++co) t[co] = fmaxf(t[co], 0.f);
+            }
+            store_row<4>(tptr(a.y2, g, row), t);
+        } else if (COUT == 8 && a.pw_mode == 2) {
+            float t[4], u[4];
+#pragma unroll
+            for (int co = 0; co < 4; ++co) t[co] = 0.f;
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+                for (int co = 0; co < 4; ++co) t[co] = fmaf(o[(COUT == 8 ? 4 : 0) + ci], s_pw[ci * 4 + co], t[co]);
+            load_row<4>(tptr(a.mask2, g, row), u);
+#pragma unroll
+            for (int co = 0; co < 4; ++co) t[co] = u[co] > 0.f ? t[co] : 0.f;
+            store_row<4>(tptr(a.y2, g, row), t);
+        }
+    } else {
+        if (a.y.p) store_row<COUT>(tptr(a.y, g, row), o);
+        // MLP_k 8 -> 24 -> 1 (models/upsample.py:49-55,156-160); hidden units in pairs, inputs in order
+        float z = s_head[240];
+#pragma unroll
+        for (int j = 0; j < 24; j += 2) {
+            u64 h2 = *reinterpret_cast<const u64 *>(s_head + 192 + j);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ffma2_acc(h2, pack2(o[i], o[i]), *reinterpret_cast<const u64 *>(s_head + i * 24 + j));
+            float h0, h1;
+            unpack2(h2, h0, h1);
+            z = fmaf(s_head[216 + j], fmaxf(h0, 0.f), z);
+            z = fmaf(s_head[217 + j], fmaxf(h1, 0.f), z);
+        }
+        const float p = 1.f / (1.f + expf(-z));
+        const int stage = a.stage_base + g;
+        const int64_t oi = (stage - a.stage_out_base) * a.out_ld + row;
+        if (a.probs) a.probs[oi] = p;
+        if (a.cdf) a.cdf[oi] = (uint16_t)(__float2int_rn(__fmul_rn(__fsub_rn(1.f, p), 65534.f)) + 1);
+        if (a.bits_partial || a.dz) {
+            const float y = (float)((a.occ[row] >> stage) & 1u);
+            const float qv = __fsub_rn(1.f, p);
+            // nn.BCELoss clamps log at -100 (models/model_core.py:14)
+            const float lp = fmaxf(logf(p), -100.f), lq = fmaxf(logf(qv), -100.f);
+            bits += -(y * lp + (1.f - y) * lq) * 1.4426950408889634f;
+            if (a.dz) {
+                // BCELoss backward (/max((1-p)p, 1e-12)) followed by sigmoid backward (*p(1-p))
+                const float pq = qv * p;
+                a.dz[oi] = (p - y) / fmaxf(pq, 1e-12f) * pq * a.dz_scale;
+            }
+        }
+    }
+}
+
+// Per-group small arrays in shared memory: bias, fused pointwise weights, head MLP (W1 transposed [8][24], b1, w2, b2)
+template <int CIN, int COUT, int MODE>
+__device__ __forceinline__ void conv_stage_small(const ConvArgs &a, int g, float *s_b, float *s_pw, float *s_head) {
+    const int TPB = blockDim.x;
     if constexpr (MODE != 2) {
         if (a.pw_mode && threadIdx.x < 36) {
             const float *wp = a.params + a.pw_w_off[g];
@@ -210,6 +315,32 @@ __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
             s_pw[i] = v;
         }
     }
+    if (threadIdx.x < COUT)
+        s_b[threadIdx.x] = a.bias_direct ? a.bias_direct[threadIdx.x] : (a.b_off[g] >= 0 ? a.params[a.b_off[g] + threadIdx.x] : 0.f);
+    if (MODE == 2) {
+        for (int i = threadIdx.x; i < 24 * 8; i += TPB) s_head[(i & 7) * 24 + (i >> 3)] = a.params[a.w1_off[g] + i];
+        if (threadIdx.x < 24) {
+            s_head[192 + threadIdx.x] = a.params[a.b1_off[g] + threadIdx.x];
+            s_head[216 + threadIdx.x] = a.params[a.w2_off[g] + threadIdx.x];
+        }
+        if (threadIdx.x == 0) s_head[240] = a.params[a.b2_off[g]];
+    }
+}
+
+template <int CIN, int COUT, int MODE, bool CW = false>
+__global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
+    constexpr int WMAX = CW ? 4 : ((MODE == 1) ? 27 * 7 * COUT : 27 * CIN * COUT);
+    constexpr int HQ = COUT / 2;  // accumulator pairs per row
+    constexpr int CONV_RPT = ConvCfg<CIN, COUT, MODE, CW>::RPT, CONV_ROWS = ConvCfg<CIN, COUT, MODE, CW>::ROWS;
+    __shared__ __align__(16) float s_w[WMAX];
+    __shared__ float s_b[COUT];
+    // head (MODE 2): W1 transposed [8][24] so that hidden-unit pairs are adjacent, then b1[24], w2[24], b2
+    __shared__ __align__(16) float s_head[(MODE == 2) ? (24 * 8 + 24 + 24 + 4) : 4];
+    __shared__ float s_red[CONV_TPB / 32];
+    __shared__ float s_pw[(MODE == 2) ? 1 : 36];   // fused pointwise weights [in][out] + bias
+    const int g = blockIdx.y;
+    const int cin = (MODE == 1) ? (a.cin_base + g * a.cin_step) : CIN;
+    conv_stage_small<CIN, COUT, MODE>(a, g, s_b, s_pw, s_head);
     {
         const float *w = a.params + a.w_off[g];
         const int n = CW ? 0 : 27 * cin * COUT;   // CW: the weights are already in the constant bank
@@ -221,16 +352,6 @@ __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
                 const int k = i / (CIN * COUT), r = i % (CIN * COUT), ci = r / COUT, co = r % COUT;
                 s_w[i] = w[(26 - k) * CIN * COUT + co * CIN + ci];
             }
-        }
-        if (threadIdx.x < COUT)
-            s_b[threadIdx.x] = a.bias_direct ? a.bias_direct[threadIdx.x] : (a.b_off[g] >= 0 ? a.params[a.b_off[g] + threadIdx.x] : 0.f);
-        if (MODE == 2) {
-            for (int i = threadIdx.x; i < 24 * 8; i += CONV_TPB) s_head[(i & 7) * 24 + (i >> 3)] = a.params[a.w1_off[g] + i];
-            if (threadIdx.x < 24) {
-                s_head[192 + threadIdx.x] = a.params[a.b1_off[g] + threadIdx.x];
-                s_head[216 + threadIdx.x] = a.params[a.w2_off[g] + threadIdx.x];
-            }
-            if (threadIdx.x == 0) s_head[240] = a.params[a.b2_off[g]];
         }
     }
     __syncthreads();
@@ -322,112 +443,7 @@ __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
         float o[COUT];
 #pragma unroll
         for (int q = 0; q < HQ; ++q) unpack2(acc[r][q], o[2 * q], o[2 * q + 1]);
-#pragma unroll
-        for (int co = 0; co < COUT; ++co) o[co] += s_b[co];
-        if constexpr (MODE != 2) {
-            if (a.res.p) {
-                float t[COUT];
-                load_row<COUT>(tptr(a.res, g, row[r]), t);
-#pragma unroll
-                for (int co = 0; co < COUT; ++co) o[co] += t[co];
-            }
-            if (a.accum) {
-                float t[COUT];
-                load_row<COUT>(tptr(a.y, g, row[r]), t);
-#pragma unroll
-                for (int co = 0; co < COUT; ++co) o[co] += t[co];
-            }
-            if constexpr (COUT == 8) {
-                if (a.pw_mode == 3) {
-                    float xv2[4], t[8];
-                    load_row<4>(tptr(a.x2, g, row[r]), xv2);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) t[i] = 0.f;
-#pragma unroll
-                    for (int ci = 0; ci < 4; ++ci)
-#pragma unroll
-                        for (int co = 0; co < 8; ++co) t[co] = fmaf(xv2[ci], s_pw[ci * 8 + co], t[co]);
-#pragma unroll
-                    for (int co = 0; co < 8; ++co) o[co] = t[co] + o[co];
-                }
-            }
-            if (a.relu) {
-#pragma unroll
-                for (int co = 0; co < COUT; ++co) o[co] = fmaxf(o[co], 0.f);
-            }
-            if (a.rmask.p) {
-                float t[COUT];
-                load_row<COUT>(tptr(a.rmask, g, row[r]), t);
-#pragma unroll
-                for (int co = 0; co < COUT; ++co) o[co] = t[co] > 0.f ? o[co] : 0.f;
-            }
-            store_row<COUT>(tptr(a.y, g, row[r]), o);
-            if (a.pw_mode == 1) {
-                float t[4];
-#pragma unroll
-                for (int co = 0; co < 4; ++co) t[co] = 0.f;
-#pragma unroll
-                for (int ci = 0; ci < COUT; ++ci)
-#pragma unroll
-                    for (int co = 0; co < 4; ++co) t[co] = fmaf(o[ci], s_pw[ci * 4 + co], t[co]);
-#pragma unroll
-                for (int co = 0; co < 4; ++co) t[co] += s_pw[32 + co];
-                if (a.res2.p) {
-                    float u[4];
-                    load_row<4>(tptr(a.res2, g, row[r]), u);
-#pragma unroll
-                    for (int co = 0; co < 4; ++co) t[co] += u[co];
-                }
-                if (a.pw_relu) {
-#pragma unroll
-                    for (int co = 0; co < 4; ++co) t[co] = fmaxf(t[co], 0.f);
-                }
-                store_row<4>(tptr(a.y2, g, row[r]), t);
-            } else if (COUT == 8 && a.pw_mode == 2) {
-                float t[4], u[4];
-#pragma unroll
-                for (int co = 0; co < 4; ++co) t[co] = 0.f;
-#pragma unroll
-                for (int ci = 0; ci < 4; ++ci)
-#pragma unroll
-                    for (int co = 0; co < 4; ++co) t[co] = fmaf(o[(COUT == 8 ? 4 : 0) + ci], s_pw[ci * 4 + co], t[co]);
-                load_row<4>(tptr(a.mask2, g, row[r]), u);
-#pragma unroll
-                for (int co = 0; co < 4; ++co) t[co] = u[co] > 0.f ? t[co] : 0.f;
-                store_row<4>(tptr(a.y2, g, row[r]), t);
-            }
-        } else {
-            if (a.y.p) store_row<COUT>(tptr(a.y, g, row[r]), o);
-            // MLP_k 8 -> 24 -> 1 (models/upsample.py:49-55,156-160); hidden units in pairs, inputs in order
-            float z = s_head[240];
-#pragma unroll
-            for (int j = 0; j < 24; j += 2) {
-                u64 h2 = *reinterpret_cast<const u64 *>(s_head + 192 + j);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) ffma2_acc(h2, pack2(o[i], o[i]), *reinterpret_cast<const u64 *>(s_head + i * 24 + j));
-                float h0, h1;
-                unpack2(h2, h0, h1);
-                z = fmaf(s_head[216 + j], fmaxf(h0, 0.f), z);
-                z = fmaf(s_head[217 + j], fmaxf(h1, 0.f), z);
-            }
-            const float p = 1.f / (1.f + expf(-z));
-            const int stage = a.stage_base + g;
-            const int64_t oi = (stage - a.stage_out_base) * a.out_ld + row[r];
-            if (a.probs) a.probs[oi] = p;
-            if (a.cdf) a.cdf[oi] = (uint16_t)(__float2int_rn(__fmul_rn(__fsub_rn(1.f, p), 65534.f)) + 1);
-            if (a.bits_partial || a.dz) {
-                const float y = (float)((a.occ[row[r]] >> stage) & 1u);
-                const float qv = __fsub_rn(1.f, p);
-                // nn.BCELoss clamps log at -100 (models/model_core.py:14)
-                const float lp = fmaxf(logf(p), -100.f), lq = fmaxf(logf(qv), -100.f);
-                bits += -(y * lp + (1.f - y) * lq) * 1.4426950408889634f;
-                if (a.dz) {
-                    // BCELoss backward (/max((1-p)p, 1e-12)) followed by sigmoid backward (*p(1-p))
-                    const float pq = qv * p;
-                    a.dz[oi] = (p - y) / fmaxf(pq, 1e-12f) * pq * a.dz_scale;
-                }
-            }
-        }
+        conv_epilogue_row<CIN, COUT, MODE>(a, g, row[r], o, s_b, s_pw, s_head, bits);
     }
     if (MODE == 2 && a.bits_partial) {
 #pragma unroll
@@ -443,6 +459,155 @@ __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// 3x3x3 sparse convolution over pair lists ("P" variant of conv27_kernel; float inputs, MODE 0 and 2).
+// The lane = row kernel above executes all 27 offsets for every row and multiplies by zero where a neighbour is
+// missing -- 14.3 of 27 offsets are occupied on a surface, 47 % of its FMAs are wasted.  Here ONE WARP owns a 256-row
+// tile and walks its 27 pair lists (RowMap::pair_list) offset by offset, 32 pairs at a time, every lane one
+// (output row, neighbour row) pair:
+//   * the weights of the current offset live in REGISTERS (CIN x COUT values, loaded once per offset with uniform
+//     loads) -- no per-pair weight traffic at all, which the lane = row mapping cannot do (every lane needs all 27);
+//   * the accumulators of the tile live in shared memory (256 x COUT floats per warp, bank-swizzled so consecutive rows
+//     are conflict-free); a pair reads its row, adds x W[k], writes it back.  Within an offset every output row occurs
+//     at most once, and offsets are processed in the lane = row kernel's order, so each output element sees exactly its
+//     FMA sequence (column-major offsets over the PRESENT ones, ci ascending; absent offsets add an exact zero
+//     there): the two kernels are bit-identical;
+//   * no block barrier in the accumulation: warps are independent; the epilogue (conv_epilogue_row) then runs lane = row
+//     over the tile.
+// `wsrc[g]` points to the group's weights in the layout of the consuming launch, [27][CIN][COUT] (forward: the
+// parameters themselves; grad-input: the mirrored / transposed copy made by bank_stage_kernel).
+// ------------------------------------------------------------------------------------------------
+constexpr int CP_T = 256;     // rows per warp = one pair-list tile
+constexpr int CP_WPB = 2;     // warps per block (small blocks: 541 blocks for a loot frame balance over 148 SMs)
+
+struct ConvPArgs {
+    ConvArgs c;
+    const float *wsrc[MAXG];
+};
+
+template <int CIN, int COUT, int MODE>
+__global__ void __launch_bounds__(32 * CP_WPB) conv27p_kernel(const ConvPArgs pa) {
+    static_assert(MODE == 0 || MODE == 2, "bit inputs stay on the lane = row kernel");
+    const ConvArgs &a = pa.c;
+    constexpr int HQ = COUT / 2, NB = CP_T / 32;
+    __shared__ __align__(128) float s_acc[CP_WPB][CP_T * COUT];
+    __shared__ float s_b[COUT];
+    __shared__ __align__(16) float s_head[(MODE == 2) ? (24 * 8 + 24 + 24 + 4) : 4];
+    __shared__ float s_red[CP_WPB];
+    __shared__ float s_pw[(MODE == 2) ? 1 : 36];
+    const int g = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    conv_stage_small<CIN, COUT, MODE>(a, g, s_b, s_pw, s_head);
+    __syncthreads();
+
+    const int64_t tile = blockIdx.x * (int64_t)CP_WPB + warp;
+    const int64_t row0 = tile * CP_T;
+    const bool have = row0 < a.map.n_rows;
+    float *acc = s_acc[warp];
+    // accumulator row o, half h (floats 4h..4h+3) lives at acc[o * COUT + 4 * (h ^ swz(o))]: eight consecutive 32-byte rows
+    // then cover all eight 16-byte bank groups with one half (see RawRow)
+    auto half_at = [&](int o, int h) -> float * { return acc + o * COUT + ((COUT == 8) ? 4 * (h ^ ((o >> 2) & 1)) : 0); };
+    float bits = 0.f;
+    if (have) {
+#pragma unroll
+        for (int j = 0; j < NB * COUT / 4; ++j) reinterpret_cast<float4 *>(acc)[j * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float *xg = a.x.p + g * a.x.gs + a.x.off;
+        const int xld = a.x.ld;
+        const int my_cnt = lane < 27 ? a.map.pair_cnt[tile * 32 + lane] : 0;
+        const uint32_t *lists = a.map.pair_list + tile * 27 * CP_T;
+        __syncwarp();
+#pragma unroll 1
+        for (int kk = 0; kk < 27; ++kk) {
+            const int k = (kk / 3) + 9 * (kk % 3);   // the lane = row kernel's order: column c = 0..8, then dz = -1, 0, +1 (k = c + 9 j)
+            const int cnt = __shfl_sync(0xffffffffu, my_cnt, k);
+            if (cnt == 0) continue;
+            // entries of this offset (up to 8 per lane), all loads in flight at once
+            uint32_t e[NB];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) e[j] = (j * 32 + lane < cnt) ? lists[k * CP_T + j * 32 + lane] : 0xffffffffu;
+            // weights of offset k -> registers (uniform addresses: one broadcast load per 16 bytes)
+            u64 w[CIN][HQ];
+            {
+                const ulonglong2 *wp = reinterpret_cast<const ulonglong2 *>(pa.wsrc[g] + k * CIN * COUT);
+#pragma unroll
+                for (int i = 0; i < CIN; ++i)
+#pragma unroll
+                    for (int q = 0; q < HQ; q += 2) {
+                        const ulonglong2 t = __ldg(wp + (i * HQ + q) / 2);
+                        w[i][q] = t.x, w[i][q + 1] = t.y;
+                    }
+            }
+            float xv[CIN];
+            auto gather = [&](uint32_t ent) {
+                if (ent != 0xffffffffu) gather_row<CIN>(xg + (int64_t)(ent & 0xffffffu) * xld, xv);
+            };
+            gather(e[0]);
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                if (j * 32 >= cnt) break;
+                const uint32_t ent = e[j];
+                float xc[CIN];
+#pragma unroll
+                for (int i = 0; i < CIN; ++i) xc[i] = xv[i];
+                if (j + 1 < NB && (j + 1) * 32 < cnt) gather(e[j + 1]);      // next batch's rows while this one multiplies
+                if (ent != 0xffffffffu) {
+                    const int o = (int)(ent >> 24);
+                    u64 ac[HQ];
+                    if constexpr (COUT == 8) {
+                        const ulonglong2 t0 = *reinterpret_cast<const ulonglong2 *>(half_at(o, 0));
+                        const ulonglong2 t1 = *reinterpret_cast<const ulonglong2 *>(half_at(o, 1));
+                        ac[0] = t0.x, ac[1] = t0.y, ac[2] = t1.x, ac[3] = t1.y;
+                    } else {
+                        const ulonglong2 t0 = *reinterpret_cast<const ulonglong2 *>(half_at(o, 0));
+                        ac[0] = t0.x, ac[1] = t0.y;
+                    }
+#pragma unroll
+                    for (int i = 0; i < CIN; ++i) {
+                        const u64 xx = pack2(xc[i], xc[i]);
+#pragma unroll
+                        for (int q = 0; q < HQ; ++q) ffma2_acc(ac[q], xx, w[i][q]);
+                    }
+                    if constexpr (COUT == 8) {
+                        *reinterpret_cast<ulonglong2 *>(half_at(o, 0)) = make_ulonglong2(ac[0], ac[1]);
+                        *reinterpret_cast<ulonglong2 *>(half_at(o, 1)) = make_ulonglong2(ac[2], ac[3]);
+                    } else {
+                        *reinterpret_cast<ulonglong2 *>(half_at(o, 0)) = make_ulonglong2(ac[0], ac[1]);
+                    }
+                }
+            }
+            __syncwarp();   // the next offset may touch any row of the tile
+        }
+        // epilogue, lane = row
+#pragma unroll 1
+        for (int j = 0; j < NB; ++j) {
+            const int rl = j * 32 + lane;
+            const int64_t row = row0 + rl;
+            if (row >= a.map.n_rows) continue;
+            float o[COUT];
+            {
+                const float4 t0 = *reinterpret_cast<const float4 *>(half_at(rl, 0));
+                o[0] = t0.x, o[1] = t0.y, o[2] = t0.z, o[3] = t0.w;
+                if constexpr (COUT == 8) {
+                    const float4 t1 = *reinterpret_cast<const float4 *>(half_at(rl, 1));
+                    o[4] = t1.x, o[5] = t1.y, o[6] = t1.z, o[7] = t1.w;
+                }
+            }
+            conv_epilogue_row<CIN, COUT, MODE>(a, g, row, o, s_b, s_pw, s_head, bits);
+        }
+    }
+    if (MODE == 2 && a.bits_partial) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, o);
+        if (lane == 0) s_red[warp] = bits;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+#pragma unroll
+            for (int w2 = 0; w2 < CP_WPB; ++w2) t += s_red[w2];
+            a.bits_partial[blockIdx.y * gridDim.x + blockIdx.x] = t;
+        }
+    }
+}
 
 // Stage the weights of a set of conv launches in the layout their kernels read (forward: as stored; grad-input:
 // W'[k][ci][co] = W_f[26-k][co][ci]) into a global buffer, fill after fill; net.cu copies a fill into the bank
