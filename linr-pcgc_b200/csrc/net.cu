@@ -345,10 +345,11 @@ struct BankCtx {   // lives for one linr_net_forward(train) / linr_net_backward 
 };
 thread_local BankCtx *t_bank = nullptr;
 
-// Stage the items of fills [f0, f1) of this call's parameters into `stage` (the pair-list conv kernel reads them from
-// there; the constant-bank kernels get them copied into the bank fill by fill) and try to take the bank.
+// Take the bank for this call and stage the items of fills [f0, f1) of its parameters in the layouts the launches read;
+// launch_conv copies a fill into the bank right before the first launch that needs it.  Returns false (the call's
+// launches then read their weights from shared memory) when the bank is busy.
 bool bank_begin(BankCtx &ctx, const Layout &L, const float *params, float *stage, int f0, int f1, cudaStream_t s) {
-    if (!stage) return false;
+    if (!stage || !bank_claim(s)) return false;
     BankItems items;
     items.n = 0;
     for (int f = 0; f < 8; ++f) items.fill_base[f] = L.fill_base[f];
@@ -359,8 +360,7 @@ bool bank_begin(BankCtx &ctx, const Layout &L, const float *params, float *stage
         ProfScope prof(K_REDUCE, items.n, s);
         bank_stage_kernel<<<items.n, 256, 0, s>>>(params, items, stage);
     }
-    ctx.L = &L, ctx.stage = stage, ctx.cur_fill = -1, ctx.stream = s;
-    ctx.have_bank = bank_claim(s);
+    ctx.L = &L, ctx.stage = stage, ctx.cur_fill = -1, ctx.stream = s, ctx.have_bank = true;
     t_bank = &ctx;
     return true;
 }
@@ -391,39 +391,6 @@ template <int CIN, int COUT, int MODE>
 int launch_conv(const ConvArgs &a, int G, cudaStream_t s) {
     if (a.map.n_rows <= 0) return 0;
     constexpr int cls = MODE == 2 ? K_CONVHEAD : MODE == 1 ? K_CONVBITS : (CIN == 8 ? (COUT == 8 ? K_CONV88 : K_CONV84) : (COUT == 8 ? K_CONV48 : K_CONV44));
-    if constexpr (MODE != 1) {
-        // pair-list kernel: needs the lists, 32-byte aligned plain rows, and the weights in the launch's layout in global
-        // memory (forward: the parameters themselves; grad-input: this call's staged mirrored copy)
-        static const bool no_p = getenv("LINR_NO_PAIRCONV") != nullptr;
-        bool ok = !no_p && a.map.pair_cnt && a.map.pair_list && a.x.p && a.x.ld == CIN && (a.x.off % CIN) == 0 && (a.x.gs % CIN) == 0 &&
-                  (reinterpret_cast<uintptr_t>(a.x.p) & (4 * CIN - 1)) == 0;
-        ConvPArgs pa;
-        if (ok) {
-            for (int g = 0; g < G && ok; ++g) {
-                if (!a.flip) {
-                    pa.wsrc[g] = a.params + a.w_off[g];
-                } else {
-                    const BankItem *hit = nullptr;
-                    if (t_bank && !a.bias_direct)
-                        for (const BankItem &it : t_bank->L->bank)
-                            if (it.w_off == a.w_off[g] && it.flip == 1) {
-                                hit = &it;
-                                break;
-                            }
-                    if (!hit) ok = false;
-                    else pa.wsrc[g] = t_bank->stage + t_bank->L->fill_base[hit->fill] + hit->dst;
-                }
-                ok = ok && (reinterpret_cast<uintptr_t>(pa.wsrc[g]) & 15) == 0;
-            }
-        }
-        if (ok) {
-            pa.c = a;
-            dim3 grid((unsigned)ceil_div64(a.map.n_rows, CP_T * CP_WPB), (unsigned)G);
-            ProfScope prof(cls, a.map.n_rows * G, s);
-            conv27p_kernel<CIN, COUT, MODE><<<grid, 32 * CP_WPB, 0, s>>>(pa);
-            return (int)grid.x;
-        }
-    }
     if (MODE != 1 && t_bank && t_bank->have_bank && !a.bias_direct) {
         // every group's weights must sit in ONE fill of the plan; otherwise this launch stays on shared memory
         ConvArgs b = a;

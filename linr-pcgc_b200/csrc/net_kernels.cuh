@@ -182,8 +182,7 @@ __device__ __forceinline__ void issue_ranges(const StagePlan &pl, const float *x
 }
 
 // Everything after the 27-offset accumulation of ONE output row `o` (bias, residual / accumulate, fused kernel_size-1
-// convs, ReLU / ReLU mask, store; MODE 2: MLP_k + sigmoid + CDF + bits + backward seed).  Shared by the lane = row
-// kernel and the pair-list kernel, so both produce the same bits.
+// convs, ReLU / ReLU mask, store; MODE 2: MLP_k + sigmoid + CDF + bits + backward seed).
 template <int CIN, int COUT, int MODE>
 __device__ __forceinline__ void conv_epilogue_row(const ConvArgs &a, int g, int64_t row, float (&o)[COUT], const float *s_b,
                                                   const float *s_pw, const float *s_head, float &bits) {
@@ -459,155 +458,6 @@ __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
     }
 }
 
-
-// ------------------------------------------------------------------------------------------------
-// 3x3x3 sparse convolution over pair lists ("P" variant of conv27_kernel; float inputs, MODE 0 and 2).
-// The lane = row kernel above executes all 27 offsets for every row and multiplies by zero where a neighbour is
-// missing -- 14.3 of 27 offsets are occupied on a surface, 47 % of its FMAs are wasted.  Here ONE WARP owns a 256-row
-// tile and walks its 27 pair lists (RowMap::pair_list) offset by offset, 32 pairs at a time, every lane one
-// (output row, neighbour row) pair:
-//   * the weights of the current offset live in REGISTERS (CIN x COUT values, loaded once per offset with uniform
-//     loads) -- no per-pair weight traffic at all, which the lane = row mapping cannot do (every lane needs all 27);
-//   * the accumulators of the tile live in shared memory (256 x COUT floats per warp, bank-swizzled so consecutive rows
-//     are conflict-free); a pair reads its row, adds x W[k], writes it back.  Within an offset every output row occurs
-//     at most once, and offsets are processed in the lane = row kernel's order, so each output element sees exactly its
-//     FMA sequence (column-major offsets over the PRESENT ones, ci ascending; absent offsets add an exact zero
-//     there): the two kernels are bit-identical;
-//   * no block barrier in the accumulation: warps are independent; the epilogue (conv_epilogue_row) then runs lane = row
-//     over the tile.
-// `wsrc[g]` points to the group's weights in the layout of the consuming launch, [27][CIN][COUT] (forward: the
-// parameters themselves; grad-input: the mirrored / transposed copy made by bank_stage_kernel).
-// ------------------------------------------------------------------------------------------------
-constexpr int CP_T = 256;     // rows per warp = one pair-list tile
-constexpr int CP_WPB = 2;     // warps per block (small blocks: 541 blocks for a loot frame balance over 148 SMs)
-
-struct ConvPArgs {
-    ConvArgs c;
-    const float *wsrc[MAXG];
-};
-
-template <int CIN, int COUT, int MODE>
-__global__ void __launch_bounds__(32 * CP_WPB) conv27p_kernel(const ConvPArgs pa) {
-    static_assert(MODE == 0 || MODE == 2, "bit inputs stay on the lane = row kernel");
-    const ConvArgs &a = pa.c;
-    constexpr int HQ = COUT / 2, NB = CP_T / 32;
-    __shared__ __align__(128) float s_acc[CP_WPB][CP_T * COUT];
-    __shared__ float s_b[COUT];
-    __shared__ __align__(16) float s_head[(MODE == 2) ? (24 * 8 + 24 + 24 + 4) : 4];
-    __shared__ float s_red[CP_WPB];
-    __shared__ float s_pw[(MODE == 2) ? 1 : 36];
-    const int g = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    conv_stage_small<CIN, COUT, MODE>(a, g, s_b, s_pw, s_head);
-    __syncthreads();
-
-    const int64_t tile = blockIdx.x * (int64_t)CP_WPB + warp;
-    const int64_t row0 = tile * CP_T;
-    const bool have = row0 < a.map.n_rows;
-    float *acc = s_acc[warp];
-    // accumulator row o, half h (floats 4h..4h+3) lives at acc[o * COUT + 4 * (h ^ swz(o))]: eight consecutive 32-byte rows
-    // then cover all eight 16-byte bank groups with one half (see RawRow)
-    auto half_at = [&](int o, int h) -> float * { return acc + o * COUT + ((COUT == 8) ? 4 * (h ^ ((o >> 2) & 1)) : 0); };
-    float bits = 0.f;
-    if (have) {
-#pragma unroll
-        for (int j = 0; j < NB * COUT / 4; ++j) reinterpret_cast<float4 *>(acc)[j * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float *xg = a.x.p + g * a.x.gs + a.x.off;
-        const int xld = a.x.ld;
-        const int my_cnt = lane < 27 ? a.map.pair_cnt[tile * 32 + lane] : 0;
-        const uint32_t *lists = a.map.pair_list + tile * 27 * CP_T;
-        __syncwarp();
-#pragma unroll 1
-        for (int kk = 0; kk < 27; ++kk) {
-            const int k = (kk / 3) + 9 * (kk % 3);   // the lane = row kernel's order: column c = 0..8, then dz = -1, 0, +1 (k = c + 9 j)
-            const int cnt = __shfl_sync(0xffffffffu, my_cnt, k);
-            if (cnt == 0) continue;
-            // entries of this offset (up to 8 per lane), all loads in flight at once
-            uint32_t e[NB];
-#pragma unroll
-            for (int j = 0; j < NB; ++j) e[j] = (j * 32 + lane < cnt) ? lists[k * CP_T + j * 32 + lane] : 0xffffffffu;
-            // weights of offset k -> registers (uniform addresses: one broadcast load per 16 bytes)
-            u64 w[CIN][HQ];
-            {
-                const ulonglong2 *wp = reinterpret_cast<const ulonglong2 *>(pa.wsrc[g] + k * CIN * COUT);
-#pragma unroll
-                for (int i = 0; i < CIN; ++i)
-#pragma unroll
-                    for (int q = 0; q < HQ; q += 2) {
-                        const ulonglong2 t = __ldg(wp + (i * HQ + q) / 2);
-                        w[i][q] = t.x, w[i][q + 1] = t.y;
-                    }
-            }
-            float xv[CIN];
-            auto gather = [&](uint32_t ent) {
-                if (ent != 0xffffffffu) gather_row<CIN>(xg + (int64_t)(ent & 0xffffffu) * xld, xv);
-            };
-            gather(e[0]);
-#pragma unroll
-            for (int j = 0; j < NB; ++j) {
-                if (j * 32 >= cnt) break;
-                const uint32_t ent = e[j];
-                float xc[CIN];
-#pragma unroll
-                for (int i = 0; i < CIN; ++i) xc[i] = xv[i];
-                if (j + 1 < NB && (j + 1) * 32 < cnt) gather(e[j + 1]);      // next batch's rows while this one multiplies
-                if (ent != 0xffffffffu) {
-                    const int o = (int)(ent >> 24);
-                    u64 ac[HQ];
-                    if constexpr (COUT == 8) {
-                        const ulonglong2 t0 = *reinterpret_cast<const ulonglong2 *>(half_at(o, 0));
-                        const ulonglong2 t1 = *reinterpret_cast<const ulonglong2 *>(half_at(o, 1));
-                        ac[0] = t0.x, ac[1] = t0.y, ac[2] = t1.x, ac[3] = t1.y;
-                    } else {
-                        const ulonglong2 t0 = *reinterpret_cast<const ulonglong2 *>(half_at(o, 0));
-                        ac[0] = t0.x, ac[1] = t0.y;
-                    }
-#pragma unroll
-                    for (int i = 0; i < CIN; ++i) {
-                        const u64 xx = pack2(xc[i], xc[i]);
-#pragma unroll
-                        for (int q = 0; q < HQ; ++q) ffma2_acc(ac[q], xx, w[i][q]);
-                    }
-                    if constexpr (COUT == 8) {
-                        *reinterpret_cast<ulonglong2 *>(half_at(o, 0)) = make_ulonglong2(ac[0], ac[1]);
-                        *reinterpret_cast<ulonglong2 *>(half_at(o, 1)) = make_ulonglong2(ac[2], ac[3]);
-                    } else {
-                        *reinterpret_cast<ulonglong2 *>(half_at(o, 0)) = make_ulonglong2(ac[0], ac[1]);
-                    }
-                }
-            }
-            __syncwarp();   // the next offset may touch any row of the tile
-        }
-        // epilogue, lane = row
-#pragma unroll 1
-        for (int j = 0; j < NB; ++j) {
-            const int rl = j * 32 + lane;
-            const int64_t row = row0 + rl;
-            if (row >= a.map.n_rows) continue;
-            float o[COUT];
-            {
-                const float4 t0 = *reinterpret_cast<const float4 *>(half_at(rl, 0));
-                o[0] = t0.x, o[1] = t0.y, o[2] = t0.z, o[3] = t0.w;
-                if constexpr (COUT == 8) {
-                    const float4 t1 = *reinterpret_cast<const float4 *>(half_at(rl, 1));
-                    o[4] = t1.x, o[5] = t1.y, o[6] = t1.z, o[7] = t1.w;
-                }
-            }
-            conv_epilogue_row<CIN, COUT, MODE>(a, g, row, o, s_b, s_pw, s_head, bits);
-        }
-    }
-    if (MODE == 2 && a.bits_partial) {
-#pragma unroll
-        for (int o = 16; o; o >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, o);
-        if (lane == 0) s_red[warp] = bits;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float t = 0.f;
-#pragma unroll
-            for (int w2 = 0; w2 < CP_WPB; ++w2) t += s_red[w2];
-            a.bits_partial[blockIdx.y * gridDim.x + blockIdx.x] = t;
-        }
-    }
-}
 
 // Stage the weights of a set of conv launches in the layout their kernels read (forward: as stored; grad-input:
 // W'[k][ci][co] = W_f[26-k][co][ci]) into a global buffer, fill after fill; net.cu copies a fill into the bank

@@ -73,26 +73,6 @@ def _frames(L):
     return [("mid", small), ("loot", big)]
 
 
-def test_pair_list_conv_is_bit_identical(L):
-    """conv27p_kernel (one pair per lane, weights in registers, accumulators in shared memory) against the lane = row
-    kernel it replaces: the same FMA sequence per output element, so the outputs must be equal bit for bit -- the
-    encoder (batched, pair lists) and the decoder (per scale, no lists) rely on it."""
-    gen = torch.Generator(device="cuda").manual_seed(3)
-    for name, fr in _frames(L):
-        t, t0 = fr.tables, _no_ranges(fr.tables)
-        n = t.n_rows
-        for cin, cout in ((8, 8), (8, 4), (4, 4), (4, 8)):
-            x = torch.randn(n, cin, generator=gen, device="cuda")
-            W = torch.randn(27, cin, cout, generator=gen, device="cuda") * 0.2
-            b = torch.randn(cout, generator=gen, device="cuda")
-            for relu in (False, True):
-                y, y0 = L.net.spconv27_fwd(x, W, b, t, relu=relu), L.net.spconv27_fwd(x, W, b, t0, relu=relu)
-                assert torch.equal(y, y0), (name, cin, cout)
-            # a row without any neighbour but itself, and an all-zero input, keep the +0 accumulator start
-            z = L.net.spconv27_fwd(torch.zeros_like(x), W, None, t)
-            assert torch.equal(z, torch.zeros_like(z)) and not torch.signbit(z).any()
-
-
 def test_weight_gradient_v3_matches_v2_and_is_reproducible(L):
     gen = torch.Generator(device="cuda").manual_seed(4)
     for name, fr in _frames(L):
