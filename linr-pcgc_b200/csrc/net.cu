@@ -386,22 +386,11 @@ bool opt_in_smem(const void *kernel, int bytes, bool (&done)[64]) {
     return true;
 }
 
-// The staged (bulk-copy) variant needs the tile ranges and a plain [rows, ld] array of 16-byte aligned rows
-template <int CIN>
-bool can_stage(const ConvArgs &a) {
-    static const bool off = getenv("LINR_NO_CONV_STAGING") != nullptr;
-    return !off && a.map.tile_rng && a.x.p && (a.x.ld == CIN || (CIN == 4 && a.x.ld == 8)) && (a.x.off & 3) == 0 && (a.x.gs & 3) == 0 &&
-           (reinterpret_cast<uintptr_t>(a.x.p) & 15) == 0;
-}
-
 // returns gridDim.x of the launch (the head kernel writes one bit-count partial per block)
 template <int CIN, int COUT, int MODE>
 int launch_conv(const ConvArgs &a, int G, cudaStream_t s) {
     if (a.map.n_rows <= 0) return 0;
     constexpr int cls = MODE == 2 ? K_CONVHEAD : MODE == 1 ? K_CONVBITS : (CIN == 8 ? (COUT == 8 ? K_CONV88 : K_CONV84) : (COUT == 8 ? K_CONV48 : K_CONV44));
-    bool st = false;
-    if constexpr (MODE != 1) st = can_stage<CIN>(a);
-    const size_t xs = st ? (size_t)XS_ROWS * a.x.ld * 4 : 0;
     if (MODE != 1 && t_bank && t_bank->have_bank && !a.bias_direct) {
         // every group's weights must sit in ONE fill of the plan; otherwise this launch stays on shared memory
         ConvArgs b = a;
@@ -423,29 +412,15 @@ int launch_conv(const ConvArgs &a, int G, cudaStream_t s) {
                                         0, cudaMemcpyDeviceToDevice, s);
                 t_bank->cur_fill = fill;
             }
+            dim3 grid((unsigned)ceil_div64(a.map.n_rows, (ConvCfg<CIN, COUT, MODE, true>::ROWS)), (unsigned)G);
             ProfScope prof(cls, a.map.n_rows * G, s);
             current_ctx()->bank_launches.fetch_add(1, std::memory_order_relaxed);
-            if constexpr (MODE != 1) {
-                if (st) {
-                    dim3 grid((unsigned)ceil_div64(a.map.n_rows, (ConvCfg<CIN, COUT, MODE, true, true>::ROWS)), (unsigned)G);
-                    conv27_kernel<CIN, COUT, MODE, true, true><<<grid, CONV_TPB, xs, s>>>(b);
-                    return (int)grid.x;
-                }
-            }
-            dim3 grid((unsigned)ceil_div64(a.map.n_rows, (ConvCfg<CIN, COUT, MODE, true>::ROWS)), (unsigned)G);
             conv27_kernel<CIN, COUT, MODE, true><<<grid, CONV_TPB, 0, s>>>(b);
             return (int)grid.x;
         }
     }
-    ProfScope prof(cls, a.map.n_rows * G, s);
-    if constexpr (MODE != 1) {
-        if (st) {
-            dim3 grid((unsigned)ceil_div64(a.map.n_rows, (ConvCfg<CIN, COUT, MODE, false, true>::ROWS)), (unsigned)G);
-            conv27_kernel<CIN, COUT, MODE, false, true><<<grid, CONV_TPB, xs, s>>>(a);
-            return (int)grid.x;
-        }
-    }
     dim3 grid((unsigned)ceil_div64(a.map.n_rows, (ConvCfg<CIN, COUT, MODE>::ROWS)), (unsigned)G);
+    ProfScope prof(cls, a.map.n_rows * G, s);
     conv27_kernel<CIN, COUT, MODE><<<grid, CONV_TPB, 0, s>>>(a);
     return (int)grid.x;
 }

@@ -101,17 +101,10 @@ constexpr int CONV_TPB = 128;
 // rows per thread: the weights of an offset are read from shared memory once for all of them (the L1/shared
 // wavefront pipe, not the FMA pipe, is what saturates first).  Measured (round 1): 4 rows help every 8-channel-input
 // conv; the 4-channel-input and bit-input convs are gather-bound and lose occupancy with more rows.
-// ST ("staged") variant.  Offsets are processed dx-major (dx = -1, 0, +1; inside a slab pass the columns dy = -1, 0, +1,
-// inside a column dz = -1, 0, +1) by EVERY variant of the kernel, so that a pass touches one neighbour row range only
-// (RowMap::tile_rng: rows are x-major sorted, the neighbours of a 512-row tile with one dx sit in ~1.1 x 512 consecutive
-// rows).  The staged variant copies that range into shared memory with one bulk (TMA) copy per pass and reads the nine
-// gathers of the pass from there: a 256-bit gather of 32 rows walks >= 8 L1 lines at ~2 cycles each, the same rows cost
-// 2 x 4 conflict-free shared-memory wavefronts.  Accumulators stay in registers across the three passes.
-constexpr int XS_ROWS = 1024;   // staged rows per pass (32 KB of 8-channel rows); a longer range falls back to L1 gathers
-template <int CIN, int COUT, int MODE, bool CW = false, bool ST = false>
+template <int CIN, int COUT, int MODE, bool CW = false>
 struct ConvCfg {
     // constant-bank weights cost issue slots of the uniform datapath instead of L1 wavefronts: always 4 rows
-    static constexpr int RPT = (ST || CW || (CIN == 8 && MODE != 1) || (CIN == 4 && COUT == 4)) ? 4 : 2;
+    static constexpr int RPT = (CW || (CIN == 8 && MODE != 1) || (CIN == 4 && COUT == 4)) ? 4 : 2;
     static constexpr int ROWS = CONV_TPB * RPT;  // rows per block
 };
 
@@ -186,37 +179,6 @@ __device__ __forceinline__ void issue_ranges(const StagePlan &pl, const float *x
 #pragma unroll
     for (int d = 0; d < 3; ++d)
         if (pl.len[d] > 0) bulk_g2s(sx + (int64_t)pl.base[d] * ld, xg + (int64_t)pl.lo[d] * ld, (uint32_t)pl.len[d] * ld * 4u, bar);
-}
-
-// One staged row as raw 16-byte pieces.  8-channel rows are 32 bytes: eight consecutive rows would hit only four of
-// the eight 16-byte bank groups with their first halves, so rows 4..7 of every eight read their halves in the
-// opposite order (conflict-free for consecutive rows; resolved with two selects per half) ...
-template <int C>
-struct RawRow {
-    float4 u[C / 4];
-    int sw;
-};
-template <int C>
-__device__ __forceinline__ void raw_load(const float *base, int p, int ld, RawRow<C> &r) {
-    const float *q = base + p * ld;
-    if constexpr (C == 8) {
-        r.sw = (p >> 2) & 1;
-        r.u[0] = *reinterpret_cast<const float4 *>(q + 4 * r.sw);
-        r.u[1] = *reinterpret_cast<const float4 *>(q + 4 * (r.sw ^ 1));
-    } else {
-        r.sw = 0;
-        r.u[0] = *reinterpret_cast<const float4 *>(q);
-    }
-}
-// ... and in channel order
-template <int C>
-__device__ __forceinline__ void raw_resolve(const RawRow<C> &r, float (&v)[C]) {
-    if constexpr (C == 8) {
-        const float4 lo = r.sw ? r.u[1] : r.u[0], hi = r.sw ? r.u[0] : r.u[1];
-        v[0] = lo.x, v[1] = lo.y, v[2] = lo.z, v[3] = lo.w, v[4] = hi.x, v[5] = hi.y, v[6] = hi.z, v[7] = hi.w;
-    } else {
-        v[0] = r.u[0].x, v[1] = r.u[0].y, v[2] = r.u[0].z, v[3] = r.u[0].w;
-    }
 }
 
 // Everything after the 27-offset accumulation of ONE output row `o` (bias, residual / accumulate, fused kernel_size-1
@@ -364,15 +326,11 @@ __device__ __forceinline__ void conv_stage_small(const ConvArgs &a, int g, float
     }
 }
 
-template <int CIN, int COUT, int MODE, bool CW = false, bool ST = false>
+template <int CIN, int COUT, int MODE, bool CW = false>
 __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
     constexpr int WMAX = CW ? 4 : ((MODE == 1) ? 27 * 7 * COUT : 27 * CIN * COUT);
     constexpr int HQ = COUT / 2;  // accumulator pairs per row
-    constexpr int CONV_RPT = ConvCfg<CIN, COUT, MODE, CW, ST>::RPT, CONV_ROWS = ConvCfg<CIN, COUT, MODE, CW, ST>::ROWS;
-    static_assert(!ST || MODE != 1, "bit inputs are gathered as single bytes: nothing to stage");
-    extern __shared__ __align__(128) float dyn_sx[];   // ST: the staged neighbour row range of the current pass
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ int s_rng[3][2];                         // ST: first row and row count of the range of each pass (count 0: not staged)
+    constexpr int CONV_RPT = ConvCfg<CIN, COUT, MODE, CW>::RPT, CONV_ROWS = ConvCfg<CIN, COUT, MODE, CW>::ROWS;
     __shared__ __align__(16) float s_w[WMAX];
     __shared__ float s_b[COUT];
     // head (MODE 2): W1 transposed [8][24] so that hidden-unit pairs are adjacent, then b1[24], w2[24], b2
@@ -395,34 +353,7 @@ __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
             }
         }
     }
-    if constexpr (ST) {
-        if (threadIdx.x == 0) {
-            mbar_init(&s_bar, 1);
-            mbar_init_fence();
-            const int64_t row0 = blockIdx.x * (int64_t)CONV_ROWS;
-            const int64_t t0 = row0 >> 7, t1 = (min(row0 + CONV_ROWS, a.map.n_rows) + 127) >> 7;
-            int lo[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, hi[3] = {0, 0, 0};
-            if (a.map.tile_rng) {
-                for (int64_t t = t0; t < t1; ++t) {
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) {
-                        const int l = a.map.tile_rng[t * 6 + 2 * d], h = a.map.tile_rng[t * 6 + 2 * d + 1];
-                        if (h > l) lo[d] = min(lo[d], l), hi[d] = max(hi[d], h);
-                    }
-                }
-            }
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                const bool ok = hi[d] > lo[d] && hi[d] - lo[d] <= XS_ROWS;
-                s_rng[d][0] = ok ? lo[d] : 0, s_rng[d][1] = ok ? hi[d] - lo[d] : 0;
-            }
-        }
-    }
     __syncthreads();
-    const int xld = a.x.ld;
-    [[maybe_unused]] bool staged = false;
-    [[maybe_unused]] int dlt = 0;
-    [[maybe_unused]] uint32_t phase = 0;
 
     int64_t row[CONV_RPT];
     bool live[CONV_RPT];
@@ -437,24 +368,7 @@ __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
         for (int q = 0; q < HQ; ++q) acc[r][q] = 0ull;
     }
 #pragma unroll 1
-    for (int cc = 0; cc < 9; ++cc) {
-        const int d = cc / 3, c = d + 3 * (cc % 3);   // slab pass d (dx = d - 1), column c = (dx+1) + 3 (dy+1)
-        if constexpr (ST) {
-            if (cc % 3 == 0) {
-                __syncthreads();                       // every warp is done with the previous pass's range
-                staged = s_rng[d][1] > 0;
-                dlt = -s_rng[d][0];
-                if (staged) {
-                    if (threadIdx.x == 0) {
-                        const uint32_t bytes = (uint32_t)s_rng[d][1] * xld * 4u;
-                        mbar_arrive_expect_tx(&s_bar, bytes);
-                        bulk_g2s(dyn_sx, a.x.p + g * a.x.gs + a.x.off + (int64_t)s_rng[d][0] * xld, bytes, &s_bar);
-                    }
-                    mbar_wait(&s_bar, phase & 1u);
-                    ++phase;
-                }
-            }
-        }
+    for (int c = 0; c < 9; ++c) {
         // (measured, round 1: loading the anchors one or two columns ahead, or prefetching the next column's
         // neighbour rows into L2, does not pay -- the gathers themselves are the exposed latency)
         uint32_t m3[CONV_RPT];
@@ -486,10 +400,6 @@ __global__ void __launch_bounds__(CONV_TPB) conv27_kernel(const ConvArgs a) {
                         const unsigned o = a.occ[nb[r]];
 #pragma unroll
                         for (int i = 0; i < 7; ++i) xv[r][i] = ((o >> i) & 1u) ? 1.f : 0.f;
-                    } else if (ST && staged) {
-                        RawRow<CIN> rr;
-                        raw_load<CIN>(dyn_sx, nb[r] + dlt, xld, rr);
-                        raw_resolve<CIN>(rr, xv[r]);
                     } else {
                         gather_row<CIN>(tptr(a.x, g, nb[r]), xv[r]);
                     }
@@ -825,6 +735,37 @@ struct BwdW3Cfg {
     static constexpr int V = CI * COUT, VP = V <= 32 ? 32 : 64;
     static_assert(STAGE % 128 == 0, "stages keep the 128-byte alignment of the bank swizzle");
 };
+
+// One staged row as raw 16-byte pieces.  8-channel rows are 32 bytes: eight consecutive rows would hit only four of
+// the eight 16-byte bank groups with their first halves, so rows 4..7 of every eight read their halves in the
+// opposite order (conflict-free for consecutive rows; resolved with two selects per half) ...
+template <int C>
+struct RawRow {
+    float4 u[C / 4];
+    int sw;
+};
+template <int C>
+__device__ __forceinline__ void raw_load(const float *base, int p, int ld, RawRow<C> &r) {
+    const float *q = base + p * ld;
+    if constexpr (C == 8) {
+        r.sw = (p >> 2) & 1;
+        r.u[0] = *reinterpret_cast<const float4 *>(q + 4 * r.sw);
+        r.u[1] = *reinterpret_cast<const float4 *>(q + 4 * (r.sw ^ 1));
+    } else {
+        r.sw = 0;
+        r.u[0] = *reinterpret_cast<const float4 *>(q);
+    }
+}
+// ... and in channel order
+template <int C>
+__device__ __forceinline__ void raw_resolve(const RawRow<C> &r, float (&v)[C]) {
+    if constexpr (C == 8) {
+        const float4 lo = r.sw ? r.u[1] : r.u[0], hi = r.sw ? r.u[0] : r.u[1];
+        v[0] = lo.x, v[1] = lo.y, v[2] = lo.z, v[3] = lo.w, v[4] = hi.x, v[5] = hi.y, v[6] = hi.z, v[7] = hi.w;
+    } else {
+        v[0] = r.u[0].x, v[1] = r.u[0].y, v[2] = r.u[0].z, v[3] = r.u[0].w;
+    }
+}
 
 template <int CIN, int COUT, int MODE, int DLD>
 __global__ void __launch_bounds__(32 * (BW3_NW + 1), 1) conv27_bwd_w3_kernel(const BwdWArgs a) {
