@@ -10,9 +10,10 @@ per-frame forward + backward + Adam) because its parameters, Adam moments and le
 (network forward, 16-bit CDFs to the host, range coder).
   N = 1 : the three GOPs one after the other on one GPU.
   N > 1 : dist.plan_job -- GOP 0 stage-split over all N GPUs (each rank computes its share of the 8 autoregressive stages of
-          every frame, ONE all-reduce of the flat 219 kB gradient per frame, identical fused Adam on every rank: the
-          reference's one-optimiser-step-per-frame semantics are kept), then GOPs 1 and 2 at the same time on two halves of
-          the GPUs, each stage-split over its half.  Fixed total work: "scaling": "strong".
+          every frame; the first rank also owns SCE + block_in, broadcasts its output and receives the reduced gradient
+          of it; ONE all-reduce of the flat 219 kB gradient per frame, identical fused Adam on every rank: the reference's
+          one-optimiser-step-per-frame semantics are kept), then GOPs 1 and 2 at the same time on two halves of the GPUs,
+          each stage-split over its half.  Fixed total work: "scaling": "strong".
   value : inputs (prepared frames) resident in HBM when the timed region starts; whole-job seconds / 96 frames.
   e2e   : the same job fed pinned HOST point arrays: H2D copy, octree / kernel-map preparation, overfit, encode, bitstreams
           collected on rank 0 -- all inside the timed region.
@@ -215,7 +216,7 @@ def workload_config(args, n, G):
         par = "1 GPU, GOPs one after the other"
     else:
         ph = D.plan_job(G, n)
-        par = ("GOP 0 stage-split over %d GPUs (gradient all-reduce per frame), then %s" %
+        par = ("GOP 0 stage-split over %d GPUs (g broadcast, dg reduce, gradient all-reduce per frame), then %s" %
                (len(ph[0][0][0]), "; ".join("GOPs %s stage-split over GPUs %d-%d" % (g, r[0], r[-1]) for r, g in ph[1]) if len(ph) > 1 else "-"))
     return {"workload": f"{args.shape}-shaped synthetic {bits}-bit surface, ~{pts // 1000}k pts/frame, gop_size {args.frames}, "
                         f"{G} GOPs = {G * args.frames} frames, {args.epochs} epochs/GOP, overfit + model quantisation + encode ({cfg})",
@@ -348,8 +349,7 @@ class Job:
         for g, ranks in self.mine:
             key = tuple(ranks)
             if key not in self.trainers:
-                self.trainers[key] = GopTrainer(self.S, dev, seed=8807, max_rows=self.max_rows,
-                                                stages=D.stage_range(len(ranks), ranks.index(rank)), group=D.group_for(ranks))
+                self.trainers[key] = GopTrainer(self.S, dev, seed=8807, max_rows=self.max_rows, ranks=ranks, group=D.group_for(ranks))
         self.pipeline = pipeline
 
     def step(self, from_host: bool = False, encode: bool = True):

@@ -180,20 +180,32 @@ int linr_net_forward(const float *d_params, int scale_num, const linr_rows *rows
 int linr_net_backward(const float *d_params, int scale_num, const linr_rows *rows, float *d_grad, void *d_ws,
                       size_t ws_bytes, void *stream);
 
-/* The same two passes restricted to the stages [stage_lo, stage_hi) of the 8 (a "stage split" of ONE frame over several
- * GPUs, SURVEY.md 8(e)(i): the reference steps the optimiser once per frame, main.py:305-321, so frames cannot be dealt
- * to ranks without changing the result; the 8 stages of a frame can).  A rank runs SCE + block_in (replicated), the LDFE
- * blocks outter_blocks[k-1] and the heads k of ITS stages (models/upsample.py:203-216).  _forward_stages: d_probs / d_cdf
- * rows of other stages are left untouched, d_bits is the bit count of the range.  _backward_stages: d_grad is overwritten
- * with the gradient contribution of the range -- zeros for the parameters of other stages, and for SCE / block_in the
- * part that flows through this range's dg = sum_k dh_k (the backward pass is linear in dg).  The SUM over a partition
- * of [0,8) equals linr_net_backward's gradient up to fp32 summation order: one all-reduce(sum) of the flat 219 kB
- * vector, then the same fused Adam step on every rank. */
-int linr_net_forward_stages(const float *d_params, int scale_num, const linr_rows *rows, int stage_lo, int stage_hi, int train,
-                            float loss_scale, float *d_probs, uint16_t *d_cdf, double *d_bits, void *d_ws, size_t ws_bytes,
-                            void *stream);
-int linr_net_backward_stages(const float *d_params, int scale_num, const linr_rows *rows, int stage_lo, int stage_hi,
-                             float *d_grad, void *d_ws, size_t ws_bytes, void *stream);
+/* The same two passes restricted to the stages [stage_lo, stage_hi) of the 8, and cut into phases: a "stage split" of ONE
+ * frame over several GPUs.  The reference steps the optimiser once per frame (main.py:305-321), so
+ * frames cannot be dealt to ranks without changing the result; the 8 stages of a frame can: stage k needs
+ * g = block_in(SCE) and its own LDFE block outter_blocks[k-1] + head k (models/upsample.py:203-216).  One rank of the
+ * group owns SCE + block_in; the phases let the caller put the two exchanges of the split between the kernels:
+ *   forward  phases (bit mask): 1 GDFE  SCE + block_in -> g           (owner; then g is broadcast, [n_rows,8] floats)
+ *                               2 PRE   ConvA + inner layers of the range's LDFE blocks (occupancy bits in: no g needed,
+ *                                       overlaps the broadcast)
+ *                               4 POST  ConvB of those blocks + g, the heads of the range, d_probs / d_cdf rows of the
+ *                                       range (others untouched), d_bits = bit count of the range
+ *   backward phases (bit mask): 1 HEADS heads of the range, dh_k, dg = sum over the range of dh_k  (then dg is reduced
+ *                                       to the owner, [n_rows,8] floats)
+ *                               2 LDFE  the range's LDFE blocks (overlaps the reduce)
+ *                               4 GDFE  block_in + SCE from the dg in the workspace (owner)
+ *                               8 FINAL chunk partials -> d_grad (overwritten): zeros for parameters this rank did not
+ *                                       touch; own_gdfe != 0 adds block_in + SCE
+ * The SUM of d_grad over the ranks of a partition of [0,8) equals linr_net_backward's gradient up to fp32 summation order:
+ * one all-reduce(sum) of the flat 219 kB vector, then the same fused Adam step on every rank.  phases 7 / 15 with
+ * own_gdfe 1 on the range [0,8) are linr_net_forward / linr_net_backward.  linr_net_ws_offsets gives the byte offsets of
+ * g and dg inside a workspace carved for n_rows (both [n_rows,8] fp32; dg is -1 without train). */
+int linr_net_forward_stages(const float *d_params, int scale_num, const linr_rows *rows, int stage_lo, int stage_hi, int phases,
+                            int train, float loss_scale, float *d_probs, uint16_t *d_cdf, double *d_bits, void *d_ws,
+                            size_t ws_bytes, void *stream);
+int linr_net_backward_stages(const float *d_params, int scale_num, const linr_rows *rows, int stage_lo, int stage_hi, int phases,
+                             int own_gdfe, float *d_grad, void *d_ws, size_t ws_bytes, void *stream);
+int linr_net_ws_offsets(int64_t n_rows, int train, int scale_num, int64_t *h_g_bytes, int64_t *h_dg_bytes);
 
 /* Sequential decoding (CNP.decode, models/upsample.py:249-295), one coordinate set at a time:
  *  _begin: SCE + block_in (GDFE);  _stage k: [LDFE_{k-1} on the k bits decoded so far] + SConv_k + MLP_k

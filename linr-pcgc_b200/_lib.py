@@ -58,8 +58,9 @@ SIGNATURES = {
     "linr_net_ws_bytes": (_SZ, [_I64, _I]),
     "linr_net_forward": (_I, [_P, _I, _RP, _I, _F, _P, _P, _P, _P, _SZ, _P]),
     "linr_net_backward": (_I, [_P, _I, _RP, _P, _P, _SZ, _P]),
-    "linr_net_forward_stages": (_I, [_P, _I, _RP, _I, _I, _I, _F, _P, _P, _P, _P, _SZ, _P]),
-    "linr_net_backward_stages": (_I, [_P, _I, _RP, _I, _I, _P, _P, _SZ, _P]),
+    "linr_net_forward_stages": (_I, [_P, _I, _RP, _I, _I, _I, _I, _F, _P, _P, _P, _P, _SZ, _P]),
+    "linr_net_backward_stages": (_I, [_P, _I, _RP, _I, _I, _I, _I, _P, _P, _SZ, _P]),
+    "linr_net_ws_offsets": (_I, [_I64, _I, _I, C.POINTER(_I64), C.POINTER(_I64)]),
     "linr_net_decode_begin": (_I, [_P, _I, _RP, _P, _SZ, _P]),
     "linr_net_decode_stage": (_I, [_P, _I, _RP, _I, _P, _P, _P, _SZ, _P]),
     "linr_occ_set_stage": (_I, [_P, _P, _I64, _I, _P]),

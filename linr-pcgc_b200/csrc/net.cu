@@ -676,12 +676,23 @@ BlockBufs bufs_at(const NetWs &w, int first) {
     return BlockBufs{w.ob_y + first * R * 8, w.ob_t1 + first * R * 4, w.ob_t0 + first * R * 4, w.ob_t2 + first * R * 4, w.ob_z + first * R * 8};
 }
 
-static int net_forward_impl(const float *d_params, int scale_num, const linr_rows *rows, int lo, int hi, int train, float loss_scale,
-                            float *d_probs, uint16_t *d_cdf, double *d_bits, void *d_ws, size_t ws_bytes, void *stream) {
+// Phases of a training iteration (stage split with ONE rank owning block_in, include/linr_b200.h):
+//   forward : FWD_GDFE  SCE + block_in -> g (= hh[0])
+//             FWD_PRE   ConvA + inner layers of the range's LDFE blocks (they read occupancy bits, not g)
+//             FWD_POST  ConvB of those blocks (+ g), the heads of the range, the bit count
+//   backward: BWD_HEADS heads, dh_k, dg = sum over the range of dh_k
+//             BWD_LDFE  the range's LDFE blocks (their inputs are bits: nothing flows further)
+//             BWD_GDFE  block_in + SCE from the dg found in the workspace (the caller has summed it over the ranks)
+//             BWD_FINAL chunk partials -> d_grad over the parameter ranges this rank wrote (own_gdfe: block_in + SCE too)
+enum { FWD_GDFE = 1, FWD_PRE = 2, FWD_POST = 4, FWD_ALL = 7, BWD_HEADS = 1, BWD_LDFE = 2, BWD_GDFE = 4, BWD_FINAL = 8, BWD_ALL = 15 };
+
+static int net_forward_impl(const float *d_params, int scale_num, const linr_rows *rows, int lo, int hi, int phases, int train,
+                            float loss_scale, float *d_probs, uint16_t *d_cdf, double *d_bits, void *d_ws, size_t ws_bytes, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     int rc = check_rows(rows, scale_num, true);
     if (rc) return rc;
     LINR_REQUIRE(lo >= 0 && lo < hi && hi <= 8, "stage range [%d,%d) is not inside [0,8)", lo, hi);
+    LINR_REQUIRE(phases > 0 && (phases & ~FWD_ALL) == 0, "forward phase mask %d out of range", phases);
     const Layout &L = layout_for(scale_num);
     const int64_t R = rows->n_rows;
     NetWs w = carve_net(d_ws, ws_bytes, R, train, L.total, L.S);
@@ -690,7 +701,7 @@ static int net_forward_impl(const float *d_params, int scale_num, const linr_row
         return LINR_ENOMEM;
     }
     if (R == 0) {
-        if (d_bits) LINR_CHECK_CUDA(cudaMemsetAsync(d_bits, 0, sizeof(double), s));
+        if (d_bits && (phases & FWD_POST)) LINR_CHECK_CUDA(cudaMemsetAsync(d_bits, 0, sizeof(double), s));
         return LINR_OK;
     }
     const RowMap m = map_of(rows);
@@ -698,41 +709,51 @@ static int net_forward_impl(const float *d_params, int scale_num, const linr_row
     BankCtx bank_ctx;
     BankScope bank_scope;
     if (train) bank_begin(bank_ctx, L, d_params, w.stage, 0, 4, s);   // training forward: weights via the constant bank
-    {  // SCE
-        SceArgs a = sce_args(d_params, L, rows);
-        a.f0 = T(w.f0, 0, 8);
-        ProfScope prof(K_SCE, R, s);
-        sce_fwd_kernel<<<(unsigned)ceil_div64(R, SCE_TPB), SCE_TPB, 0, s>>>(a);
+    if (phases & FWD_GDFE) {
+        {  // SCE
+            SceArgs a = sce_args(d_params, L, rows);
+            a.f0 = T(w.f0, 0, 8);
+            ProfScope prof(K_SCE, R, s);
+            sce_fwd_kernel<<<(unsigned)ceil_div64(R, SCE_TPB), SCE_TPB, 0, s>>>(a);
+        }
+        // g = block_in(f0) -> hh[0] (group 7 of the block activation arrays)
+        block_A_forward(d_params, &L.bin, 1, m, false, nullptr, 0, 0, T(w.f0, 0, 8), w.bi_y, w.bi_t1, s);
     }
-    // ConvA of the GDFE block (float input f0, group 7) and of the LDFE blocks (occupancy bits, teacher forcing)
-    block_A_forward(d_params, &L.bin, 1, m, false, nullptr, 0, 0, T(w.f0, 0, 8), w.bi_y, w.bi_t1, s);
-    if (jh > jl)
+    if ((phases & FWD_PRE) && jh > jl)   // ConvA of the LDFE blocks (occupancy bits, teacher forcing)
         block_A_forward(d_params, L.ob + jl, jh - jl, m, true, rows->d_occ, jl + 1, 1, TN(), w.ob_y + jl * R * 8, w.ob_t1 + jl * R * 4, s);
     // the five inner layers of the blocks in multi-group launches
-    for_block_groups(jl, jh, [&](int first, int count) { block_mid_forward(d_params, L.blk8 + first, count, m, bufs_at(w, first), s); });
-    // ConvB: g = block_in(f0) -> hh[0], then hh[k+1] = g + LDFE_k(occ[:, :k+1])
-    block_B_forward(d_params, &L.bin, 1, m, w.bi_z, T(w.hh, 0, 8), TN(), s);
-    if (jh > jl)
-        block_B_forward(d_params, L.ob + jl, jh - jl, m, w.ob_z + jl * R * 8, T(w.hh + (jl + 1) * R * 8, R * 8, 8), T(w.hh, 0, 8), s);
-    // heads of the stages [lo, hi)
-    const bool want_bits = d_bits != nullptr || train;
-    const int head_gx = head_forward(d_params, L, m, lo, hi - lo, T(w.hh + lo * R * 8, R * 8, 8), train ? w.hc + lo * R * 8 : nullptr,
-                                     rows->d_occ, d_probs, d_cdf, train ? w.dzs : nullptr, loss_scale * 1.4426950408889634f,
-                                     want_bits ? w.bits_partial : nullptr, 0, s);
-    if (d_bits) {
-        ProfScope prof(K_REDUCE, 1, s);
-        bits_finalize_kernel<<<1, 256, 0, s>>>(w.bits_partial, head_gx * (hi - lo), d_bits);
+    {
+        const bool gd = phases & FWD_GDFE, pre = (phases & FWD_PRE) && jh > jl;
+        if (gd && pre) for_block_groups(jl, jh, [&](int first, int count) { block_mid_forward(d_params, L.blk8 + first, count, m, bufs_at(w, first), s); });
+        else if (gd) block_mid_forward(d_params, L.blk8 + 7, 1, m, bufs_at(w, 7), s);
+        else if (pre) block_mid_forward(d_params, L.blk8 + jl, jh - jl, m, bufs_at(w, jl), s);
+    }
+    if (phases & FWD_GDFE) block_B_forward(d_params, &L.bin, 1, m, w.bi_z, T(w.hh, 0, 8), TN(), s);
+    if (phases & FWD_POST) {
+        // ConvB: hh[k+1] = g + LDFE_k(occ[:, :k+1])
+        if (jh > jl)
+            block_B_forward(d_params, L.ob + jl, jh - jl, m, w.ob_z + jl * R * 8, T(w.hh + (jl + 1) * R * 8, R * 8, 8), T(w.hh, 0, 8), s);
+        // heads of the stages [lo, hi)
+        const bool want_bits = d_bits != nullptr || train;
+        const int head_gx = head_forward(d_params, L, m, lo, hi - lo, T(w.hh + lo * R * 8, R * 8, 8), train ? w.hc + lo * R * 8 : nullptr,
+                                         rows->d_occ, d_probs, d_cdf, train ? w.dzs : nullptr, loss_scale * 1.4426950408889634f,
+                                         want_bits ? w.bits_partial : nullptr, 0, s);
+        if (d_bits) {
+            ProfScope prof(K_REDUCE, 1, s);
+            bits_finalize_kernel<<<1, 256, 0, s>>>(w.bits_partial, head_gx * (hi - lo), d_bits);
+        }
     }
     LINR_LAUNCH_CHECK();
     return LINR_OK;
 }
 
-static int net_backward_impl(const float *d_params, int scale_num, const linr_rows *rows, int lo, int hi, float *d_grad, void *d_ws,
-                             size_t ws_bytes, void *stream) {
+static int net_backward_impl(const float *d_params, int scale_num, const linr_rows *rows, int lo, int hi, int phases, int own_gdfe,
+                             float *d_grad, void *d_ws, size_t ws_bytes, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     int rc = check_rows(rows, scale_num, true);
     if (rc) return rc;
     LINR_REQUIRE(lo >= 0 && lo < hi && hi <= 8, "stage range [%d,%d) is not inside [0,8)", lo, hi);
+    LINR_REQUIRE(phases > 0 && (phases & ~BWD_ALL) == 0, "backward phase mask %d out of range", phases);
     const Layout &L = layout_for(scale_num);
     const int64_t R = rows->n_rows;
     const int P = L.total;
@@ -741,16 +762,23 @@ static int net_backward_impl(const float *d_params, int scale_num, const linr_ro
         linr_set_error("linr_net_backward: workspace too small (%zu < %zu)", ws_bytes, w.used);
         return LINR_ENOMEM;
     }
-    const bool partial_range = lo != 0 || hi != 8;
-    if (R == 0 || partial_range) LINR_CHECK_CUDA(cudaMemsetAsync(d_grad, 0, sizeof(float) * P, s));   // parameters of other stages: zero
+    const bool partial_range = lo != 0 || hi != 8 || !own_gdfe;
+    if ((phases & BWD_FINAL) && (R == 0 || partial_range))
+        LINR_CHECK_CUDA(cudaMemsetAsync(d_grad, 0, sizeof(float) * P, s));   // parameters this rank did not touch: zero
     if (R == 0) return LINR_OK;
     const RowMap m = map_of(rows);
     const int jl = (lo > 1 ? lo : 1) - 1, jh = hi - 1, G = hi - lo;
     BankCtx bank_ctx;
     BankScope bank_scope;
-    bank_begin(bank_ctx, L, d_params, w.stage, 4, 8, s);
-    // heads: dc, MLP weight partials, SConv weight partials, dh_k
-    {
+    if (phases & (BWD_HEADS | BWD_LDFE | BWD_GDFE)) bank_begin(bank_ctx, L, d_params, w.stage, 4, 8, s);
+    BlockGrads gr{w.g_dz, w.g_dt0, w.g_dy, w.g_dt2, w.g_dt1};
+    auto blocks_backward = [&](int first, int count) {
+        BlockGrads g2{gr.dz + first * R * 8, gr.dt0 + first * R * 4, gr.dy + first * R * 8, gr.dt2 + first * R * 4, gr.dt1 + first * R * 4};
+        // output gradients: dhh[j+1] for LDFE block j, dg = dhh[8] for block_in = group 7
+        block_Bmid_backward(d_params, L.blk8 + first, count, m, w, P, bufs_at(w, first), g2, T(w.dhh + (first + 1) * R * 8, R * 8, 8), s);
+    };
+    if (phases & BWD_HEADS) {
+        // heads: dc, MLP weight partials, SConv weight partials, dh_k
         HeadBwdArgs a;
         memset(&a, 0, sizeof(a));
         a.n_rows = R, a.params = d_params;
@@ -764,57 +792,61 @@ static int net_backward_impl(const float *d_params, int scale_num, const linr_ro
             ProfScope prof(K_HEADBWD, R * G, s);
             head_bwd_rows_kernel<<<dim3((unsigned)ceil_div64(R, 128 * HEAD_RPT), (unsigned)G), 128, 0, s>>>(a);
         }
-        ProfScope prof(K_HEADBWD, R * G, s);
-        head_bwd_w_kernel<<<dim3((unsigned)w.n_chunks, (unsigned)G), 256, 0, s>>>(a);
-    }
-    launch_bwd_w<8, 8, 0>(m, w, P, L.pr_w + lo, L.pr_b + lo, G, T(w.hh + lo * R * 8, R * 8, 8), T(w.dc + lo * R * 8, R * 8, 8), nullptr, 0, 0, s);
-    {
-        ConvArgs a = conv_args(m, d_params);
-        for (int g = 0; g < G; ++g) a.w_off[g] = L.pr_w[lo + g];
-        a.flip = 1, a.x = T(w.dc + lo * R * 8, R * 8, 8), a.y = T(w.dhh + lo * R * 8, R * 8, 8);
-        launch_conv<8, 8, 0>(a, G, s);
-    }
-    // every h_k contains g: dg = sum over this range's stages of dh_k (the backward pass is linear in dg, so the
-    // per-rank pieces of a stage split add up in the gradient all-reduce)
-    {
+        {
+            ProfScope prof(K_HEADBWD, R * G, s);
+            head_bwd_w_kernel<<<dim3((unsigned)w.n_chunks, (unsigned)G), 256, 0, s>>>(a);
+        }
+        launch_bwd_w<8, 8, 0>(m, w, P, L.pr_w + lo, L.pr_b + lo, G, T(w.hh + lo * R * 8, R * 8, 8), T(w.dc + lo * R * 8, R * 8, 8), nullptr, 0, 0, s);
+        {
+            ConvArgs ca = conv_args(m, d_params);
+            for (int g = 0; g < G; ++g) ca.w_off[g] = L.pr_w[lo + g];
+            ca.flip = 1, ca.x = T(w.dc + lo * R * 8, R * 8, 8), ca.y = T(w.dhh + lo * R * 8, R * 8, 8);
+            launch_conv<8, 8, 0>(ca, G, s);
+        }
+        // every h_k contains g: dg = sum over this range's stages of dh_k.  The backward pass is linear in dg, so the ranks
+        // of a stage split add their pieces (one reduce of [R,8] floats) before the owner of block_in runs BWD_GDFE.
         ProfScope prof(K_REDUCE, R, s);
         sum_groups_kernel<<<(unsigned)ceil_div64(R * 2, 256), 256, 0, s>>>(w.dhh + lo * R * 8, R * 8, G, R * 2, w.dg);
     }
-    // ConvB + inner layers of the blocks (output gradients: dhh[j+1] for LDFE block j, dg = dhh[8] for GDFE = group 7)
-    BlockGrads gr{w.g_dz, w.g_dt0, w.g_dy, w.g_dt2, w.g_dt1};
-    for_block_groups(jl, jh, [&](int first, int count) {
-        BlockGrads g2{gr.dz + first * R * 8, gr.dt0 + first * R * 4, gr.dy + first * R * 8, gr.dt2 + first * R * 4, gr.dt1 + first * R * 4};
-        block_Bmid_backward(d_params, L.blk8 + first, count, m, w, P, bufs_at(w, first), g2, T(w.dhh + (first + 1) * R * 8, R * 8, 8), s);
-    });
-    // ConvA: LDFE blocks read occupancy bits (no input gradient); the GDFE block (group 7) propagates to f0
-    if (jh > jl)
-        block_A_backward(d_params, L.ob + jl, jh - jl, m, w, P, true, rows->d_occ, jl + 1, 1, TN(), T(w.g_dy + jl * R * 8, R * 8, 8), TN(), s);
-    block_A_backward(d_params, &L.bin, 1, m, w, P, false, nullptr, 0, 0, T(w.f0, 0, 8), T(w.g_dy + 7 * R * 8, 0, 8), T(w.df0, 0, 8), s);
-    // SCE
-    SceArgs sa = sce_args(d_params, L, rows);
-    sa.df0 = T(w.df0, 0, 8), sa.chunk = w.chunk;
     {
-        ProfScope prof(K_SCE, R, s);
-        sce_bwd_kernel<<<(unsigned)w.n_chunks, SCE_BWD_TPB, 0, s>>>(sa, w.sce_rec);
+        const bool ld = (phases & BWD_LDFE) && jh > jl, gd = phases & BWD_GDFE;
+        // ConvB + inner layers of the blocks
+        if (ld && gd) for_block_groups(jl, jh, blocks_backward);
+        else if (ld) blocks_backward(jl, jh - jl);
+        else if (gd) blocks_backward(7, 1);
+        // ConvA: LDFE blocks read occupancy bits (no input gradient); block_in propagates to f0
+        if (ld)
+            block_A_backward(d_params, L.ob + jl, jh - jl, m, w, P, true, rows->d_occ, jl + 1, 1, TN(), T(w.g_dy + jl * R * 8, R * 8, 8), TN(), s);
+        if (gd) {
+            block_A_backward(d_params, &L.bin, 1, m, w, P, false, nullptr, 0, 0, T(w.f0, 0, 8), T(w.g_dy + 7 * R * 8, 0, 8), T(w.df0, 0, 8), s);
+            SceArgs sa = sce_args(d_params, L, rows);
+            sa.df0 = T(w.df0, 0, 8), sa.chunk = w.chunk;
+            ProfScope prof(K_SCE, R, s);
+            sce_bwd_kernel<<<(unsigned)w.n_chunks, SCE_BWD_TPB, 0, s>>>(sa, w.sce_rec);
+        }
     }
-    {
-        ProfScope prof(K_SCE, L.S, s);
-        sce_finalize_kernel<<<(unsigned)L.S, 1024, 0, s>>>(sa, w.sce_rec, w.n_chunks, d_grad);
-    }
-    // chunk partials -> gradient, only over the parameter ranges this stage range wrote
-    auto finalize = [&](int first, int end) {
-        const int64_t cnt = end - first;
-        if (cnt <= 0) return;
-        ProfScope prof(K_REDUCE, cnt, s);
-        finalize_grad_kernel<<<(unsigned)ceil_div64(cnt, 256), 256, 0, s>>>(w.partial, P, w.n_chunks, first, cnt, d_grad);
-    };
-    if (!partial_range) {
-        finalize(L.conv_first, P);
-    } else {
-        finalize(L.conv_first, L.mlp_w1[0]);                                         // GDFE block
-        finalize(L.mlp_w1[lo], hi < 8 ? L.mlp_w1[hi] : L.pr_w[0]);                   // MLP_k of the stages
-        finalize(L.pr_w[lo], hi < 8 ? L.pr_w[hi] : L.ob[0].A_w);                     // SConv_k of the stages
-        if (jh > jl) finalize(L.ob[jl].A_w, jh < 7 ? L.ob[jh].A_w : P);              // LDFE blocks
+    if (phases & BWD_FINAL) {
+        if (own_gdfe) {
+            SceArgs sa = sce_args(d_params, L, rows);
+            sa.df0 = T(w.df0, 0, 8), sa.chunk = w.chunk;
+            ProfScope prof(K_SCE, L.S, s);
+            sce_finalize_kernel<<<(unsigned)L.S, 1024, 0, s>>>(sa, w.sce_rec, w.n_chunks, d_grad);
+        }
+        // chunk partials -> gradient, only over the parameter ranges this rank wrote
+        auto finalize = [&](int first, int end) {
+            const int64_t cnt = end - first;
+            if (cnt <= 0) return;
+            ProfScope prof(K_REDUCE, cnt, s);
+            finalize_grad_kernel<<<(unsigned)ceil_div64(cnt, 256), 256, 0, s>>>(w.partial, P, w.n_chunks, first, cnt, d_grad);
+        };
+        if (!partial_range) {
+            finalize(L.conv_first, P);
+        } else {
+            if (own_gdfe) finalize(L.conv_first, L.mlp_w1[0]);                       // block_in
+            finalize(L.mlp_w1[lo], hi < 8 ? L.mlp_w1[hi] : L.pr_w[0]);                   // MLP_k of the stages
+            finalize(L.pr_w[lo], hi < 8 ? L.pr_w[hi] : L.ob[0].A_w);                     // SConv_k of the stages
+            if (jh > jl) finalize(L.ob[jl].A_w, jh < 7 ? L.ob[jh].A_w : P);              // LDFE blocks
+        }
     }
     LINR_LAUNCH_CHECK();
     return LINR_OK;
@@ -917,22 +949,34 @@ size_t linr_net_ws_bytes(int64_t n_rows, int train) {
 
 int linr_net_forward(const float *d_params, int scale_num, const linr_rows *rows, int train, float loss_scale,
                      float *d_probs, uint16_t *d_cdf, double *d_bits, void *d_ws, size_t ws_bytes, void *stream) {
-    return net_forward_impl(d_params, scale_num, rows, 0, 8, train, loss_scale, d_probs, d_cdf, d_bits, d_ws, ws_bytes, stream);
+    return net_forward_impl(d_params, scale_num, rows, 0, 8, FWD_ALL, train, loss_scale, d_probs, d_cdf, d_bits, d_ws, ws_bytes, stream);
 }
 
 int linr_net_backward(const float *d_params, int scale_num, const linr_rows *rows, float *d_grad, void *d_ws,
                       size_t ws_bytes, void *stream) {
-    return net_backward_impl(d_params, scale_num, rows, 0, 8, d_grad, d_ws, ws_bytes, stream);
+    return net_backward_impl(d_params, scale_num, rows, 0, 8, BWD_ALL, 1, d_grad, d_ws, ws_bytes, stream);
 }
 
-int linr_net_forward_stages(const float *d_params, int scale_num, const linr_rows *rows, int stage_lo, int stage_hi, int train,
-                            float loss_scale, float *d_probs, uint16_t *d_cdf, double *d_bits, void *d_ws, size_t ws_bytes, void *stream) {
-    return net_forward_impl(d_params, scale_num, rows, stage_lo, stage_hi, train, loss_scale, d_probs, d_cdf, d_bits, d_ws, ws_bytes, stream);
+int linr_net_forward_stages(const float *d_params, int scale_num, const linr_rows *rows, int stage_lo, int stage_hi, int phases,
+                            int train, float loss_scale, float *d_probs, uint16_t *d_cdf, double *d_bits, void *d_ws, size_t ws_bytes,
+                            void *stream) {
+    return net_forward_impl(d_params, scale_num, rows, stage_lo, stage_hi, phases, train, loss_scale, d_probs, d_cdf, d_bits, d_ws,
+                            ws_bytes, stream);
 }
 
-int linr_net_backward_stages(const float *d_params, int scale_num, const linr_rows *rows, int stage_lo, int stage_hi, float *d_grad,
-                             void *d_ws, size_t ws_bytes, void *stream) {
-    return net_backward_impl(d_params, scale_num, rows, stage_lo, stage_hi, d_grad, d_ws, ws_bytes, stream);
+int linr_net_backward_stages(const float *d_params, int scale_num, const linr_rows *rows, int stage_lo, int stage_hi, int phases,
+                             int own_gdfe, float *d_grad, void *d_ws, size_t ws_bytes, void *stream) {
+    return net_backward_impl(d_params, scale_num, rows, stage_lo, stage_hi, phases, own_gdfe, d_grad, d_ws, ws_bytes, stream);
+}
+
+int linr_net_ws_offsets(int64_t n_rows, int train, int scale_num, int64_t *h_g_bytes, int64_t *h_dg_bytes) {
+    LINR_REQUIRE(scale_num >= 1 && scale_num <= MAXS, "scale_num out of range");
+    const Layout &L = layout_for(scale_num);
+    char *base = reinterpret_cast<char *>(4096);
+    NetWs w = carve_net(base, ~(size_t)0 >> 1, n_rows, train, L.total, L.S);
+    if (h_g_bytes) *h_g_bytes = reinterpret_cast<char *>(w.hh) - base;
+    if (h_dg_bytes) *h_dg_bytes = train ? reinterpret_cast<char *>(w.dg) - base : -1;
+    return LINR_OK;
 }
 
 int linr_net_decode_begin(const float *d_params, int scale_num, const linr_rows *rows, void *d_ws, size_t ws_bytes, void *stream) {

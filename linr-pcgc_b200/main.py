@@ -145,7 +145,7 @@ def overfit_one_gop(args, seq: Sequence, group: List[int], epochs: int, seed_sta
         seed = int(t.item())
     tr = GopTrainer(S, device, args.learning_rate, args.gamma, args.step_size, args.min_lr, args.decay_rate, seed=seed,
                     state=seed_state.clone() if seed_state is not None else None,
-                    max_rows=max(f.tables.n_rows for f in frames), stages=D.stage_range(parts, part), group=pg)
+                    max_rows=max(f.tables.n_rows for f in frames), ranks=ranks, group=pg)
     results, t_train = [], 0.0
     for ep in range(epochs):
         torch.cuda.synchronize()

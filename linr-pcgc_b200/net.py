@@ -26,6 +26,10 @@ def param_offsets(scale_num: int):
     return [int(buf[i]) for i in range(n)]
 
 
+FWD_GDFE, FWD_PRE, FWD_POST, FWD_ALL = 1, 2, 4, 7                      # forward phases (include/linr_b200.h)
+BWD_HEADS, BWD_LDFE, BWD_GDFE, BWD_FINAL, BWD_ALL = 1, 2, 4, 8, 15       # backward phases
+
+
 class NetRunner:
     def __init__(self, scale_num: int, max_rows: int, device, train: bool = True):
         self.lib = _lib.load()
@@ -76,8 +80,9 @@ class NetRunner:
 
     # -- teacher-forced forward over all 8 stages ---------------------------------------------------------
     def forward(self, params: torch.Tensor, t: RowTables, train: bool = False, loss_scale: float = 0.0,
-                want_probs: bool = False, want_cdf: bool = False, want_bits: bool = True, stages=(0, 8)):
-        """`stages` = (lo, hi): only the stages lo..hi-1 (one rank's share of a stage split, linr_net_forward_stages)."""
+                want_probs: bool = False, want_cdf: bool = False, want_bits: bool = True, stages=(0, 8), phases: int = FWD_ALL):
+        """`stages` = (lo, hi): only the stages lo..hi-1, `phases`: which part of the pass (one rank's share of a stage
+        split, linr_net_forward_stages)."""
         assert params.is_cuda and params.dtype == torch.float32 and params.numel() == self.P
         assert t.occ is not None, "teacher-forced forward needs the ground-truth occupancy"
         assert not train or self.train, "runner was created without training workspace"
@@ -86,7 +91,7 @@ class NetRunner:
         rows = t.rows()
         if train:
             self.lib.linr_ctx_set_current(self.ctx)
-        check(self.lib.linr_net_forward_stages(ptr(params), self.S, C.byref(rows), int(stages[0]), int(stages[1]),
+        check(self.lib.linr_net_forward_stages(ptr(params), self.S, C.byref(rows), int(stages[0]), int(stages[1]), int(phases),
                                                1 if train else 0, loss_scale,
                                                ptr(self.probs) if want_probs else None, ptr(self.cdf) if want_cdf else None,
                                                ptr(self.bits) if want_bits else None, ptr(self.ws), self.ws.numel(), stream_ptr()),
@@ -100,12 +105,30 @@ class NetRunner:
             out["cdf"] = self.cdf[: 8 * n].view(8, n)
         return out
 
-    def backward(self, params: torch.Tensor, t: RowTables, grad: torch.Tensor, stages=(0, 8)):
+    def backward(self, params: torch.Tensor, t: RowTables, grad: torch.Tensor, stages=(0, 8), phases: int = BWD_ALL,
+                 own_gdfe: bool = True):
         assert grad.is_cuda and grad.numel() >= self.P
         rows = t.rows()
         self.lib.linr_ctx_set_current(self.ctx)
-        check(self.lib.linr_net_backward_stages(ptr(params), self.S, C.byref(rows), int(stages[0]), int(stages[1]), ptr(grad),
-                                                ptr(self.ws), self.ws.numel(), stream_ptr()), "linr_net_backward_stages")
+        check(self.lib.linr_net_backward_stages(ptr(params), self.S, C.byref(rows), int(stages[0]), int(stages[1]), int(phases),
+                                                1 if own_gdfe else 0, ptr(grad), ptr(self.ws), self.ws.numel(), stream_ptr()),
+              "linr_net_backward_stages")
+
+    def exchange_views(self, n_rows: int):
+        """(g, dg): float32 [n_rows, 8] views of the workspace -- what a stage split broadcasts (g = block_in's output) and
+        reduces (dg = its gradient) between the phases."""
+        key = int(n_rows)
+        hit = self._views.get(key) if hasattr(self, "_views") else None
+        if hit is None or hit[2] is not self.ws:
+            og, od = C.c_int64(), C.c_int64()
+            check(self.lib.linr_net_ws_offsets(key, 1 if self.train else 0, self.S, C.byref(og), C.byref(od)), "linr_net_ws_offsets")
+            nb = key * 32
+            g = self.ws[og.value: og.value + nb].view(torch.float32).view(key, 8)
+            dg = self.ws[od.value: od.value + nb].view(torch.float32).view(key, 8) if od.value >= 0 else None
+            if not hasattr(self, "_views"):
+                self._views = {}
+            hit = self._views[key] = (g, dg, self.ws)
+        return hit[0], hit[1]
 
     # -- sequential decode ----------------------------------------------------------------------------------
     def decode_begin(self, params: torch.Tensor, t: RowTables):

@@ -7,10 +7,13 @@ betas .9/.999, eps 1e-8, L2 1e-4) (main.py:231-237), StepLR(step_size 32, gamma 
 parameters, Adam moments, step count and learning rate (main.py:102-104,241-246); the StepLR counter restarts with
 every GOP because the reference builds a fresh scheduler per GOP (main.py:252).
 
-Several GPUs on ONE GOP ("stage split"): every rank steps through the same frames in the same
-order and computes the stages `stages = (lo, hi)` of each frame (linr_net_forward_stages / _backward_stages); one
-all-reduce(sum) of the flat gradient per frame, then the same fused Adam step on every rank, so the parameters stay
-replicated bit for bit and the optimiser still steps once per frame exactly as the reference does.
+Several GPUs on ONE GOP ("stage split"): every rank of `ranks` steps through the same frames in the
+same order and computes its share of the 8 autoregressive stages of each frame (dist.stage_range; LDFE block + head per
+stage).  The first rank also owns SCE + block_in: it broadcasts g = block_in's output ([rows,8] floats) while the others
+already run their LDFE blocks (which read occupancy bits, not g), and receives the sum of the ranks' dg = sum_k dh_k
+(one reduce) while they run their LDFE backward.  One all-reduce(sum) of the flat 219 kB gradient per frame, then the
+same fused Adam step on every rank: the parameters stay replicated bit for bit and the optimiser still steps once per
+frame exactly as the reference does (main.py:305-321).
 """
 from __future__ import annotations
 
@@ -64,7 +67,7 @@ class GopTrainer:
     def __init__(self, scale_num: int, device="cuda", learning_rate: float = 0.01, gamma: float = 0.992,
                  step_size: int = 32, min_lr: float = 4e-4, decay_rate: float = 1e-4, seed: Optional[int] = None,
                  state: Optional[OptimState] = None, max_rows: int = 1, grad_hook: Optional[Callable] = None,
-                 stages=(0, 8), group=None):
+                 ranks: Optional[Sequence[int]] = None, group=None):
         self.S = scale_num
         self.device = torch.device(device)
         self.gamma, self.step_size, self.min_lr, self.wd = gamma, step_size, min_lr, decay_rate
@@ -78,9 +81,17 @@ class GopTrainer:
         self.grad = torch.empty(n, dtype=torch.float32, device=self.device)
         self.runner = NetRunner(scale_num, max_rows, self.device, train=True)
         self.grad_hook = grad_hook   # called with the flat gradient before the Adam step
-        self.stages = (int(stages[0]), int(stages[1]))
-        self.group = group           # torch.distributed group of the ranks that share this GOP (stage split)
-        self.split = self.stages != (0, 8)
+        # stage split: `ranks` = the global ranks that share this GOP (None / one rank: no split), `group` their process group
+        self.ranks = list(ranks) if ranks is not None and len(ranks) > 1 else None
+        self.group = group
+        self.split = self.ranks is not None
+        if self.split:
+            from . import dist as D
+            self.part = self.ranks.index(torch.distributed.get_rank())
+            self.stages = D.stage_range(len(self.ranks), self.part)
+            self.leader = self.ranks[0]          # owner of SCE + block_in
+        else:
+            self.part, self.stages, self.leader = 0, (0, 8), 0
         self.bits_log: List[torch.Tensor] = []
 
     def close(self):
@@ -100,18 +111,44 @@ class GopTrainer:
     # one frame-iteration (main.py:305-321)
     def step(self, frame: Frame, record_bits: bool = True):
         st = self.state
-        out = self.runner.forward(st.params, frame.tables, train=True, loss_scale=1.0 / frame.point_num,
-                                  want_bits=record_bits, stages=self.stages)
-        self.runner.backward(st.params, frame.tables, self.grad, stages=self.stages)
-        if self.split:
-            # sum of the per-rank stage contributions = the frame's gradient; stream-ordered, no host sync
-            torch.distributed.all_reduce(self.grad, op=torch.distributed.ReduceOp.SUM, group=self.group)
+        t, ls = frame.tables, 1.0 / frame.point_num
+        if not self.split:
+            out = self.runner.forward(st.params, t, train=True, loss_scale=ls, want_bits=record_bits)
+            self.runner.backward(st.params, t, self.grad)
+        else:
+            out = self._split_iteration(st.params, t, ls, record_bits)
         if self.grad_hook is not None:
             self.grad_hook(self.grad)
         st.step += 1
         adam_step(st.params, self.grad, st.m, st.v, st.step, st.lr, wd=self.wd)
         sched_after_step(st, self.step_size, self.gamma)
         return out.get("bits")
+
+    def _split_iteration(self, params, t, ls, record_bits):
+        """Forward + backward of this rank's stages with the two exchanges of the split between the phases; every launch
+        and both collectives are stream-ordered (no host sync)."""
+        from . import net as N
+        dist = torch.distributed
+        run, own = self.runner, self.part == 0
+        kw = dict(train=True, loss_scale=ls, stages=self.stages)
+        run.reserve(t.n_rows)
+        g, dg = run.exchange_views(t.n_rows)
+        if own:
+            run.forward(params, t, want_bits=False, phases=N.FWD_GDFE, **kw)
+        wb = dist.broadcast(g, src=self.leader, group=self.group, async_op=True)     # overlaps the LDFE blocks below
+        run.forward(params, t, want_bits=False, phases=N.FWD_PRE, **kw)
+        wb.wait()
+        out = run.forward(params, t, want_bits=record_bits, phases=N.FWD_POST, **kw)
+        run.backward(params, t, self.grad, stages=self.stages, phases=N.BWD_HEADS, own_gdfe=own)
+        wr = dist.reduce(dg, dst=self.leader, op=dist.ReduceOp.SUM, group=self.group, async_op=True)   # overlaps the LDFE backward
+        run.backward(params, t, self.grad, stages=self.stages, phases=N.BWD_LDFE, own_gdfe=own)
+        wr.wait()
+        if own:
+            run.backward(params, t, self.grad, stages=self.stages, phases=N.BWD_GDFE, own_gdfe=True)
+        run.backward(params, t, self.grad, stages=self.stages, phases=N.BWD_FINAL, own_gdfe=own)
+        # sum of the per-rank contributions = the frame's gradient
+        dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)
+        return out
 
     def end_epoch(self):
         sched_end_epoch(self.state, self.min_lr)

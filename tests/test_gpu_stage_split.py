@@ -27,6 +27,40 @@ def _cases(L, O):
     return D, [(fr, flat.cuda()), (big, P.init_flat(big.n_scales, 5).cuda())]
 
 
+def _emulated_split_iteration(L, D, run, params, t, point_num, parts, probs=None, cdf=None):
+    """One frame-iteration of a `parts`-rank stage split on ONE GPU and one workspace: the ranks' phases run one after the
+    other, the broadcast of g is a no-op (same buffer) and the reduce of dg a sum.  Returns (summed gradient, bits)."""
+    N = L.net
+    ls = 1.0 / point_num
+    g_view, dg_view = run.exchange_views(t.n_rows)
+    run.forward(params, t, train=True, loss_scale=ls, want_bits=False, stages=D.stage_range(parts, 0), phases=N.FWD_GDFE)
+    bits = 0.0
+    for part in range(parts):
+        sr = D.stage_range(parts, part)
+        run.forward(params, t, train=True, loss_scale=ls, want_bits=False, stages=sr, phases=N.FWD_PRE)
+        o = run.forward(params, t, train=True, loss_scale=ls, want_probs=probs is not None, want_cdf=cdf is not None, stages=sr,
+                        phases=N.FWD_POST)
+        if probs is not None:   # a rank's probabilities / CDFs of its own stages are the single-GPU ones bit for bit
+            assert torch.equal(o["probs"][sr[0]:sr[1]], probs[sr[0]:sr[1]]) and torch.equal(o["cdf"][sr[0]:sr[1]], cdf[sr[0]:sr[1]])
+        bits += float(o["bits"].item())
+    grad = torch.full_like(params, float("nan"))
+    dg_sum = torch.zeros_like(dg_view)
+    for part in range(parts):
+        run.backward(params, t, grad, stages=D.stage_range(parts, part), phases=N.BWD_HEADS, own_gdfe=part == 0)
+        dg_sum += dg_view
+    dg_view.copy_(dg_sum)
+    tot = torch.zeros_like(params)
+    for part in range(parts):
+        sr = D.stage_range(parts, part)
+        run.backward(params, t, grad, stages=sr, phases=N.BWD_LDFE, own_gdfe=part == 0)
+        if part == 0:
+            run.backward(params, t, grad, stages=sr, phases=N.BWD_GDFE, own_gdfe=True)
+        run.backward(params, t, grad, stages=sr, phases=N.BWD_FINAL, own_gdfe=part == 0)
+        assert torch.isfinite(grad).all()
+        tot += grad
+    return tot, bits
+
+
 def test_stage_ranges_sum_to_the_full_gradient(L, O):
     D, cases = _cases(L, O)
     for f, params in cases:
@@ -37,45 +71,35 @@ def test_stage_ranges_sum_to_the_full_gradient(L, O):
         probs, cdf, bits = o["probs"].clone(), o["cdf"].clone(), float(o["bits"].item())
         run.backward(params, t, full)
         for parts in (2, 3, 4, 8):
-            tot = torch.zeros_like(params)
-            tot_bits = 0.0
-            for part in range(parts):
-                lo, hi = D.stage_range(parts, part)
-                g = torch.full_like(params, float("nan"))
-                o = run.forward(params, t, train=True, loss_scale=1.0 / f.point_num, want_probs=True, want_cdf=True, stages=(lo, hi))
-                # a rank's probabilities / CDFs of its own stages are the single-GPU ones bit for bit
-                assert torch.equal(o["probs"][lo:hi], probs[lo:hi]) and torch.equal(o["cdf"][lo:hi], cdf[lo:hi])
-                tot_bits += float(o["bits"].item())
-                run.backward(params, t, g, stages=(lo, hi))
-                assert torch.isfinite(g).all()
-                tot += g
+            tot, tot_bits = _emulated_split_iteration(L, D, run, params, t, f.point_num, parts, probs, cdf)
             assert abs(tot_bits - bits) <= 1e-9 * abs(bits)
-            # same terms, different fp32 summation order for SCE / block_in only
+            # same terms; only dg (and through it SCE / block_in) is summed in another order
             assert (tot - full).abs().max().item() <= 2e-6 * full.abs().max().item(), parts
+        # the phased calls over the whole range are the plain passes, bit for bit
+        N = L.net
+        g2 = torch.empty_like(params)
+        for ph in (N.FWD_GDFE, N.FWD_PRE, N.FWD_POST):
+            run.forward(params, t, train=True, loss_scale=1.0 / f.point_num, want_bits=False, phases=ph)
+        for ph in (N.BWD_HEADS, N.BWD_LDFE, N.BWD_GDFE, N.BWD_FINAL):
+            run.backward(params, t, g2, phases=ph)
+        assert torch.equal(g2, full)
 
 
 def test_emulated_two_rank_training_matches_single_gpu(L, O):
     """8 optimiser steps over 4 frames: parameters of the emulated 2-rank stage split within 1e-6 of the 1-GPU run."""
-    from linr_pcgc_b200 import dist as D, params as P
+    from linr_pcgc_b200 import dist as D
     pts = L.synth.make_sequence("tiny", 4, device="cuda")
-    frames = [L.frame.prepare_frame(p, None, 64) for p in pts]
-    S = frames[0].n_scales
+    S = L.frame.prepare_frame(pts[0], None, 64).n_scales
     frames = [L.frame.prepare_frame(p, S, 64) for p in pts]
     mr = max(f.tables.n_rows for f in frames)
     ref = L.trainer.GopTrainer(S, "cuda", seed=3, max_rows=mr)
     ref.fit(frames, 2)
     st = L.trainer.GopTrainer(S, "cuda", seed=3, max_rows=mr).state      # same initial state
     run = L.net.NetRunner(S, mr, "cuda", train=True)
-    g = torch.empty_like(st.params)
     step, lr = 0, 0.01
     for _ in range(2):
         for f in frames:
-            tot = torch.zeros_like(st.params)
-            for part in range(2):
-                sr = D.stage_range(2, part)
-                run.forward(st.params, f.tables, train=True, loss_scale=1.0 / f.point_num, stages=sr)
-                run.backward(st.params, f.tables, g, stages=sr)
-                tot += g
+            tot, _ = _emulated_split_iteration(L, D, run, st.params, f.tables, f.point_num, 2)
             step += 1
             L.net.adam_step(st.params, tot, st.m, st.v, step, lr)
     assert (st.params - ref.state.params).abs().max().item() <= 1e-6
@@ -94,7 +118,7 @@ pts = synth.make_sequence("plumbing", 4, device=dev)
 frames = pipeline.prepare_gop(pts, None, 64, dev)
 S = frames[0].n_scales
 mr = max(f.tables.n_rows for f in frames)
-tr = GopTrainer(S, dev, seed=7, max_rows=mr, stages=D.stage_range(world, rank), group=None)
+tr = GopTrainer(S, dev, seed=7, max_rows=mr, ranks=list(range(world)), group=None)
 losses = tr.fit(frames, 2)
 enc = pipeline.encode_gop(frames, tr.state.params, S, 8)
 # every rank must hold the same parameters bit for bit
