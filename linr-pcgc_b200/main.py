@@ -97,11 +97,24 @@ def gop_ranges(frame_num: int, gop_size: int) -> List[List[int]]:
     return [list(range(i, min(i + gop_size, frame_num))) for i in range(0, frame_num, gop_size)]
 
 
-def save_checkpoint(path: str, state: OptimState, scale_num: int, epoch: int, loss: float, bitdepth: int):
-    views = P.named_views(state.params.detach().cpu(), scale_num)
-    torch.save({"model": dict(views), "epoch": epoch, "loss": loss, "bitdepth": bitdepth, "scale_num": scale_num,
-                "optimizer_state_dict": {"format": "linr_b200_flat_adam", "m": state.m.cpu(), "v": state.v.cpu(),
-                                         "step": state.step, "sched_step": state.sched_step, "lr": state.lr}}, path)
+def save_checkpoint(path: str, state: OptimState, scale_num: int, epoch: int, loss: float, bitdepth: int,
+                    learning_rate: float = 0.01, weight_decay: float = 1e-4):
+    """model.pth in the reference's layout (main.py:365-374): 'model' = state_dict by the reference's tensor names,
+    'optimizer_state_dict' = what torch.optim.Adam.state_dict() gives for model.parameters() in order (per-tensor step /
+    exp_avg / exp_avg_sq, one param group with lr and initial_lr), so the reference's own
+    `optimizer.load_state_dict(ckpt['optimizer_state_dict'])` (main.py:243-246) accepts a checkpoint written here."""
+    cpu = lambda t: t.detach().cpu()
+    views = P.named_views(cpu(state.params), scale_num)
+    m_views, v_views = P.named_views(cpu(state.m), scale_num), P.named_views(cpu(state.v), scale_num)
+    names = [n for n, _ in P.param_spec(scale_num)]
+    opt_state = {i: {"step": torch.tensor(float(state.step)), "exp_avg": m_views[n].clone(), "exp_avg_sq": v_views[n].clone()}
+                 for i, n in enumerate(names)}
+    group = {"lr": state.lr, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": weight_decay, "amsgrad": False, "maximize": False,
+             "foreach": None, "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": False,
+             "initial_lr": learning_rate, "params": list(range(len(names)))}
+    torch.save({"model": {n: views[n].clone() for n in names}, "epoch": epoch, "loss": loss, "bitdepth": bitdepth, "scale_num": scale_num,
+                "optimizer_state_dict": {"state": opt_state, "param_groups": [group]},
+                "linr_b200": {"sched_step": state.sched_step}}, path)
 
 
 def load_checkpoint(path: str, device) -> (OptimState, int):
@@ -110,7 +123,7 @@ def load_checkpoint(path: str, device) -> (OptimState, int):
     scale_num = int(ck.get("scale_num", model["scale_emb.weight"].shape[0]))
     flat = torch.cat([model[n].reshape(-1).float() for n, _ in P.param_spec(scale_num)]).to(device)
     opt = ck.get("optimizer_state_dict", {})
-    if opt.get("format") == "linr_b200_flat_adam":
+    if opt.get("format") == "linr_b200_flat_adam":   # round-1 checkpoints of this implementation
         st = OptimState(flat, opt["m"].to(device), opt["v"].to(device), int(opt["step"]), int(opt["sched_step"]), float(opt["lr"]))
     elif "state" in opt:  # a checkpoint written by the reference: torch.optim.Adam state per tensor, parameters() order
         ms = torch.cat([opt["state"][i]["exp_avg"].reshape(-1).float() for i in range(len(opt["state"]))]).to(device)
@@ -165,7 +178,7 @@ def overfit_one_gop(args, seq: Sequence, group: List[int], epochs: int, seed_sta
                 json.dump(results, f, indent=4)
     if args.write_pth == "True" and writer:
         save_checkpoint(os.path.join(gdir, "model.pth"), tr.state, S, epochs - 1, results[-1]["loss"] if results else 0.0,
-                        args.model_bitdepth)
+                        args.model_bitdepth, args.learning_rate, args.decay_rate)
     return tr.state, S
 
 

@@ -252,6 +252,34 @@ def test_gop_container_round_trips_and_matches_the_directory_layout(tmp_path):
         container.unpack(data[:-5])
 
 
+def test_checkpoint_is_loadable_by_torch_adam_like_the_reference(tmp_path):
+    """main.py:241-246 of the reference: `optimizer.load_state_dict(ckpt['optimizer_state_dict'])` on an Adam over
+    model.parameters() -- a model.pth written by save_checkpoint must pass through that, and come back through
+    load_checkpoint unchanged (interoperability in both directions)."""
+    from linr_pcgc_b200 import main as M, params as P
+    from linr_pcgc_b200.trainer import OptimState
+    S = 3
+    n = P.offsets(P.param_spec(S))[-1]
+    g = torch.Generator().manual_seed(1)
+    st = OptimState(torch.randn(n, generator=g), torch.randn(n, generator=g), torch.rand(n, generator=g), 37, 5, 7.5e-3)
+    path = str(tmp_path / "model.pth")
+    M.save_checkpoint(path, st, S, 9, 0.25, 8, 0.01, 1e-4)
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    spec = P.param_spec(S)
+    assert list(ck["model"].keys()) == [k for k, _ in spec] and all(tuple(ck["model"][k].shape) == tuple(shp) for k, shp in spec)
+    plist = [torch.nn.Parameter(ck["model"][k].clone()) for k, _ in spec]          # what model.parameters() yields, in order
+    opt = torch.optim.Adam(plist, lr=0.01, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+    opt.load_state_dict(ck["optimizer_state_dict"])
+    assert opt.param_groups[0]["lr"] == 7.5e-3 and opt.param_groups[0]["initial_lr"] == 0.01
+    m_back = torch.cat([opt.state[p]["exp_avg"].reshape(-1) for p in plist])
+    assert torch.equal(m_back, st.m) and float(opt.state[plist[0]]["step"]) == 37.0
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=32, gamma=0.992)          # main.py:252 on the loaded optimizer
+    assert sched.get_last_lr() == [7.5e-3]
+    back, S2 = M.load_checkpoint(path, "cpu")
+    assert S2 == S and torch.equal(back.params, st.params) and torch.equal(back.m, st.m) and torch.equal(back.v, st.v)
+    assert back.step == 37 and back.lr == 7.5e-3
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
