@@ -608,16 +608,20 @@ def finish(cx):
         cx.dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE 8-group launch over a loot-shaped frame (277,011 rows x 8 groups
-# = 2,216,088 units), from the `ncu --set full` captures summarised under profiles/ (r01e conv kernels, r01g weight
-# gradients); per unit, so it scales to the launches of this run.  None: not captured.
-NCU_TRAFFIC_SOURCE = "ncu --set full dram bytes per (row x group) unit, profiles/r01e_*, r01g_*; scaled by this run's units per launch"
-NCU_DRAM_BYTES_PER_UNIT = {
-    "conv27<8,8>": (83.960832e6 + 39.300096e6) / 2216088, "conv27<8,4>": (82.984704e6 + 18.523136e6) / 2216088,
-    "conv27<4,4>": (173.155072e6 + 58.067968e6) / 2216088, "conv27_bits<8>": (11.316992e6 + 6.055936e6) / 1939077,
-    "conv27_head": (84.780544e6 + 47.52e6) / 2216088, "bwd_w<8,8>": (153.3184e6 + 8.76288e6) / 2216088,
-    "bwd_w<4,4>": (118.37824e6 + 4.628224e6) / 2216088, "bwd_w_bits<8>": (73.083136e6 + 3.748608e6) / 1939077,
-}
+# dram__bytes_read.sum + dram__bytes_write.sum per (row x group) unit of every kernel class, from ONE `ncu --set full`
+# capture of a training iteration, written by tools/ncu_traffic_table.py (profiles/r02_traffic_per_unit.json); per unit,
+# so it scales to the launches of this run.  A class the capture does not hold has no entry (traffic: null).
+def _load_traffic():
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic_per_unit.json")))
+        return ({k: v["dram_bytes_per_unit"] for k, v in t["classes"].items()},
+                f"ncu --set full, one frame-iteration ({t['source']}, {t['rows_per_frame']} rows/frame), tools/ncu_traffic_table.py -> "
+                "profiles/r02_traffic_per_unit.json; per (row x group) unit, scaled by this run's units per launch")
+    except Exception:
+        return {}, "profiles/r02_traffic_per_unit.json missing"
+
+
+NCU_DRAM_BYTES_PER_UNIT, NCU_TRAFFIC_SOURCE = _load_traffic()
 
 
 def algorithmic_bytes(kernel: str, pbar: float) -> float:

@@ -56,6 +56,10 @@ typedef struct linr_ctx linr_ctx;
 int linr_ctx_create(int device, linr_ctx **out);
 int linr_ctx_destroy(linr_ctx *ctx);
 int linr_ctx_set_current(linr_ctx *ctx);
+/* One-shot hint for the NEXT training call through the context: it gets the same parameter values and the same workspace
+ * as the previous call of the same direction (forward / backward), so the conv weights staged by that call are still
+ * valid and are not staged again.  Used between the phases of one iteration (linr_net_*_stages); cleared by the call. */
+int linr_ctx_hint_same_params(linr_ctx *ctx);
 int64_t linr_ctx_bank_calls(const linr_ctx *ctx);
 int64_t linr_ctx_bank_launches(const linr_ctx *ctx);
 

@@ -34,6 +34,7 @@ SIGNATURES = {
     "linr_ctx_create": (_I, [_I, C.POINTER(_P)]),
     "linr_ctx_destroy": (_I, [_P]),
     "linr_ctx_set_current": (_I, [_P]),
+    "linr_ctx_hint_same_params": (_I, [_P]),
     "linr_ctx_bank_calls": (_I64, [_P]),
     "linr_ctx_bank_launches": (_I64, [_P]),
     "linr_prof_enable": (_I, [C.c_uint32]),

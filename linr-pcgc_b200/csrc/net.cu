@@ -289,6 +289,8 @@ struct linr_ctx {
     cudaEvent_t done = nullptr;               // end of this context's last training call (created on first use)
     std::atomic<int64_t> bank_launches{0};    // constant-bank (CW) conv launches made through this context
     std::atomic<int64_t> bank_calls{0};       // training calls that held the bank
+    int same_params = 0;                      // one-shot hint: the next training call sees the parameters of the previous one
+    bool staged[2] = {false, false};          // forward / backward weight layouts of those parameters are in the staging area
 };
 namespace {
 struct BankState {
@@ -349,7 +351,17 @@ thread_local BankCtx *t_bank = nullptr;
 // launch_conv copies a fill into the bank right before the first launch that needs it.  Returns false (the call's
 // launches then read their weights from shared memory) when the bank is busy.
 bool bank_begin(BankCtx &ctx, const Layout &L, const float *params, float *stage, int f0, int f1, cudaStream_t s) {
+    linr_ctx *me = current_ctx();
+    const int dir = f0 >= 4 ? 1 : 0;
+    // the caller vouches: same parameters, same workspace as its previous call -- and that call did stage them
+    const bool staged_already = me->same_params != 0 && me->staged[dir];
+    me->same_params = 0;
+    if (!staged_already) me->staged[dir] = false;
     if (!stage || !bank_claim(s)) return false;
+    ctx.L = &L, ctx.stage = stage, ctx.cur_fill = -1, ctx.stream = s, ctx.have_bank = true;
+    t_bank = &ctx;
+    if (staged_already) return true;
+    me->staged[dir] = true;
     BankItems items;
     items.n = 0;
     for (int f = 0; f < 8; ++f) items.fill_base[f] = L.fill_base[f];
@@ -360,8 +372,6 @@ bool bank_begin(BankCtx &ctx, const Layout &L, const float *params, float *stage
         ProfScope prof(K_REDUCE, items.n, s);
         bank_stage_kernel<<<items.n, 256, 0, s>>>(params, items, stage);
     }
-    ctx.L = &L, ctx.stage = stage, ctx.cur_fill = -1, ctx.stream = s, ctx.have_bank = true;
-    t_bank = &ctx;
     return true;
 }
 struct BankScope {
@@ -899,6 +909,10 @@ int linr_ctx_destroy(linr_ctx *ctx) {
 }
 int linr_ctx_set_current(linr_ctx *ctx) {
     t_ctx = ctx;
+    return LINR_OK;
+}
+int linr_ctx_hint_same_params(linr_ctx *ctx) {
+    (ctx ? ctx : current_ctx())->same_params = 1;
     return LINR_OK;
 }
 int64_t linr_ctx_bank_calls(const linr_ctx *ctx) {

@@ -80,7 +80,8 @@ class NetRunner:
 
     # -- teacher-forced forward over all 8 stages ---------------------------------------------------------
     def forward(self, params: torch.Tensor, t: RowTables, train: bool = False, loss_scale: float = 0.0,
-                want_probs: bool = False, want_cdf: bool = False, want_bits: bool = True, stages=(0, 8), phases: int = FWD_ALL):
+                want_probs: bool = False, want_cdf: bool = False, want_bits: bool = True, stages=(0, 8), phases: int = FWD_ALL,
+                same_params: bool = False):
         """`stages` = (lo, hi): only the stages lo..hi-1, `phases`: which part of the pass (one rank's share of a stage
         split, linr_net_forward_stages)."""
         assert params.is_cuda and params.dtype == torch.float32 and params.numel() == self.P
@@ -91,6 +92,8 @@ class NetRunner:
         rows = t.rows()
         if train:
             self.lib.linr_ctx_set_current(self.ctx)
+            if same_params:      # a later phase of the same iteration: the weights staged by the first phase are still valid
+                self.lib.linr_ctx_hint_same_params(self.ctx)
         check(self.lib.linr_net_forward_stages(ptr(params), self.S, C.byref(rows), int(stages[0]), int(stages[1]), int(phases),
                                                1 if train else 0, loss_scale,
                                                ptr(self.probs) if want_probs else None, ptr(self.cdf) if want_cdf else None,
@@ -106,10 +109,12 @@ class NetRunner:
         return out
 
     def backward(self, params: torch.Tensor, t: RowTables, grad: torch.Tensor, stages=(0, 8), phases: int = BWD_ALL,
-                 own_gdfe: bool = True):
+                 own_gdfe: bool = True, same_params: bool = False):
         assert grad.is_cuda and grad.numel() >= self.P
         rows = t.rows()
         self.lib.linr_ctx_set_current(self.ctx)
+        if same_params:
+            self.lib.linr_ctx_hint_same_params(self.ctx)
         check(self.lib.linr_net_backward_stages(ptr(params), self.S, C.byref(rows), int(stages[0]), int(stages[1]), int(phases),
                                                 1 if own_gdfe else 0, ptr(grad), ptr(self.ws), self.ws.numel(), stream_ptr()),
               "linr_net_backward_stages")

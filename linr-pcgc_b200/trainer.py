@@ -136,15 +136,15 @@ class GopTrainer:
         if own:
             run.forward(params, t, want_bits=False, phases=N.FWD_GDFE, **kw)
         wb = dist.broadcast(g, src=self.leader, group=self.group, async_op=True)     # overlaps the LDFE blocks below
-        run.forward(params, t, want_bits=False, phases=N.FWD_PRE, **kw)
+        run.forward(params, t, want_bits=False, phases=N.FWD_PRE, same_params=own, **kw)
         wb.wait()
-        out = run.forward(params, t, want_bits=record_bits, phases=N.FWD_POST, **kw)
+        out = run.forward(params, t, want_bits=record_bits, phases=N.FWD_POST, same_params=True, **kw)
         run.backward(params, t, self.grad, stages=self.stages, phases=N.BWD_HEADS, own_gdfe=own)
         wr = dist.reduce(dg, dst=self.leader, op=dist.ReduceOp.SUM, group=self.group, async_op=True)   # overlaps the LDFE backward
-        run.backward(params, t, self.grad, stages=self.stages, phases=N.BWD_LDFE, own_gdfe=own)
+        run.backward(params, t, self.grad, stages=self.stages, phases=N.BWD_LDFE, own_gdfe=own, same_params=True)
         wr.wait()
         if own:
-            run.backward(params, t, self.grad, stages=self.stages, phases=N.BWD_GDFE, own_gdfe=True)
+            run.backward(params, t, self.grad, stages=self.stages, phases=N.BWD_GDFE, own_gdfe=True, same_params=True)
         run.backward(params, t, self.grad, stages=self.stages, phases=N.BWD_FINAL, own_gdfe=own)
         # sum of the per-rank contributions = the frame's gradient
         dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)
