@@ -579,7 +579,7 @@ def main():
                 torch.cuda.empty_cache()
                 for shp in ("mvub10", "mvub9"):      # C5: decode-only throughput
                     extras[f"C5_decode_{shp}"] = run_decode_only(cx, args, shp, F=16, E=3, K=2, W=1)
-            if cx.world == 8 and args.shape == "loot":
+            if (cx.world == 8 or os.environ.get("LINR_BENCH_C4") == "1") and args.shape == "loot":
                 del job
                 torch.cuda.empty_cache()
                 a2 = argparse.Namespace(**vars(args))
@@ -615,7 +615,7 @@ def _load_traffic():
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic_per_unit.json")))
         return ({k: v["dram_bytes_per_unit"] for k, v in t["classes"].items()},
-                f"ncu --set full, one frame-iteration ({t['source']}, {t['rows_per_frame']} rows/frame), tools/ncu_traffic_table.py -> "
+                f"ncu dram__bytes_read/write.sum over one frame-iteration ({t['source']}, {t['rows_per_frame']} rows/frame), tools/ncu_traffic_table.py -> "
                 "profiles/r02_traffic_per_unit.json; per (row x group) unit, scaled by this run's units per launch")
     except Exception:
         return {}, "profiles/r02_traffic_per_unit.json missing"
