@@ -234,6 +234,15 @@ int linr_net_decode_scale(const float *d_params, int scale_num, const linr_rows 
                           const int64_t *h_nbytes, uint16_t *d_cdf, uint8_t *d_sym, uint16_t *h_cdf, uint8_t *h_sym,
                           void *d_ws, size_t ws_bytes, void *stream);
 
+/* The same for SEVERAL frames at once: the rows of `rows` are the concatenation of n_seg frames' parents of one scale
+ * (segment f = rows [h_seg_off[f], h_seg_off[f+1]); the caller keeps the frames apart in space, e.g. by an x offset per
+ * frame, so that no neighbourhood crosses a segment boundary).  Every stage is ONE set of launches over all frames, one
+ * CDF download, n_seg range decoders on `threads` host threads, one symbol upload: 56 launch sets and round trips per
+ * batch instead of per frame.  h_streams / h_nbytes are [n_seg][8]. */
+int linr_net_decode_scale_batch(const float *d_params, int scale_num, const linr_rows *rows, int n_seg, const int64_t *h_seg_off,
+                                const uint8_t *const *h_streams, const int64_t *h_nbytes, uint16_t *d_cdf, uint8_t *d_sym,
+                                uint16_t *h_cdf, uint8_t *h_sym, int threads, void *d_ws, size_t ws_bytes, void *stream);
+
 /* Single-layer entry points (used by the MinkowskiEngine-shaped shim and by unit tests).
  * ME.MinkowskiConvolution(kernel_size=3, stride=1) forward on one coordinate set (models/upsample.py:17,90,95):
  *   y[n,cout] = sum_k x[row(C+delta_k)] @ W[k] + bias;  W [27,cin,cout], bias [cout] or NULL; cin,cout in {4,8}. */
@@ -270,6 +279,9 @@ int linr_param_quant16(const float *d_params, int64_t n, int bitdepth, uint16_t 
  * or -(needed) if cap is too small. */
 int64_t linr_rc_encode_binary(const uint16_t *h_cdf_mid, const uint8_t *h_sym, int64_t n, uint8_t *h_out, int64_t cap);
 int linr_rc_decode_binary(const uint16_t *h_cdf_mid, const uint8_t *h_in, int64_t nbytes, uint8_t *h_sym, int64_t n);
+/* Many independent binary streams decoded at once on `threads` host threads (one stage of several frames). */
+int linr_rc_decode_binary_batch(int n_streams, const uint16_t *const *h_cdf_mid, const uint8_t *const *h_in, const int64_t *nbytes,
+                                uint8_t *const *h_sym, const int64_t *n, int threads);
 /* Many independent binary streams at once on `threads` host threads (the 8 stages x S scales of a frame,
  * models/upsample.py:219-246).  Stream i codes bit h_shift[i] of each byte of h_sym[i] (h_shift NULL: bit 0), so
  * the 8 stage streams of a scale read the packed occupancy bytes in place.  h_written[i] = bytes, or -(needed). */

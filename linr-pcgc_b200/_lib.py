@@ -75,6 +75,8 @@ SIGNATURES = {
     "linr_param_quant16": (_I, [_P, _I64, _I, _P, _P, _P, _P]),
     "linr_rc_encode_binary": (_I64, [_P, _P, _I64, _P, _I64]),
     "linr_rc_decode_binary": (_I, [_P, _P, _I64, _P, _I64]),
+    "linr_rc_decode_binary_batch": (_I, [_I, _P, _P, _P, _P, _P, _I]),
+    "linr_net_decode_scale_batch": (_I, [_P, _I, _RP, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _SZ, _P]),
     "linr_rc_encode_binary_batch": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _I]),
     "linr_rc_encode_shared": (_I64, [_P, _I, _P, _I64, _P, _I64]),
     "linr_rc_decode_shared": (_I, [_P, _I, _P, _I64, _P, _I64]),

@@ -227,6 +227,111 @@ def decode_frames(params: torch.Tensor, scale_num: int, jobs: Sequence, workers:
         idle.extend(used)
 
 
+_POPC = {}
+
+
+def decode_frames_batched(params: torch.Tensor, scale_num: int, jobs: Sequence, max_batch: int = 8, workers: int = 2,
+                          threads: Optional[int] = None) -> List[torch.Tensor]:
+    """Decode independent frames in LOCKSTEP (frames of a GOP only share the model): at every scale the parents of all
+    frames of a batch are concatenated -- frame f shifted by f * stride in x, so the frames stay sorted, unique and out
+    of each other's 3x3x3 neighbourhoods -- and every one of the 8 stages is one set of launches over all of them, one
+    CDF download, one range decoder per frame on its own host thread, one symbol upload (linr_net_decode_scale_batch).
+    A batch makes 56 launch sets and device<->host round trips instead of 56 per frame, and the launches are large
+    enough to fill the GPU (a per-frame stage of a coarse scale is a handful of blocks).  `workers` batches run at the
+    same time on their own streams and host threads, so the network passes of one overlap the range decoding of the
+    other.  Bit-identical CDFs: a row sees the same neighbours in the same order as in its own frame.
+    jobs: (all_bytes, low_coords CUDA int32 [N,3])."""
+    from concurrent.futures import ThreadPoolExecutor
+    import threading
+    if not jobs:
+        return []
+    dev = params.device
+    low_max = max(int(j[1].max().item()) if j[1].numel() else 0 for j in jobs)
+    s_max = max(len(j[0]) for j in jobs)
+    low_stride = 1 << max(1, (low_max + 2 - 1).bit_length())                  # >= low_max + 2: a gap of at least one voxel
+    fit = max(1, (1 << 20) // (low_stride << s_max))                          # coordinates stay below 2^20 at the finest level
+    B = max(1, min(max_batch, fit))
+    batches = [list(range(b0, min(b0 + B, len(jobs)))) for b0 in range(0, len(jobs), B)]
+    workers = max(1, min(workers, len(batches)))
+    threads = threads or max(B, rc.host_cores() // workers)
+    if dev not in _POPC:
+        _POPC[dev] = torch.tensor([bin(i).count("1") for i in range(256)], dtype=torch.int64, device=dev)
+    popc = _POPC[dev]
+    out: List[Optional[torch.Tensor]] = [None] * len(jobs)
+    main_stream = torch.cuda.current_stream(dev)
+    ready = torch.cuda.Event()
+    ready.record(main_stream)
+
+    key = (str(dev), scale_num)
+    idle = _ctx_pool.setdefault(key, [])          # decode contexts (workspace, pinned staging, stream) are kept across calls
+    lock = threading.Lock()
+
+    def run(worker: int, mine):
+        torch.cuda.set_device(dev)
+        with lock:
+            ctx = idle.pop() if idle else None
+        if ctx is None:
+            ctx = _DecodeCtx(scale_num, dev)
+            ctx.stream = torch.cuda.Stream(dev)
+        try:
+            with torch.cuda.stream(ctx.stream):
+                ctx.stream.wait_event(ready)
+                for idx in mine:
+                    _decode_batch(ctx, params, [jobs[i] for i in idx], s_max, low_stride, popc, threads, out, idx)
+                ctx.stream.synchronize()
+        finally:
+            with lock:
+                idle.append(ctx)
+
+    if workers == 1:
+        run(0, batches)
+    else:
+        with ThreadPoolExecutor(max_workers=workers) as pool:
+            list(pool.map(lambda w: run(w, batches[w::workers]), range(workers)))
+    return out  # type: ignore[return-value]
+
+
+def _decode_batch(ctx: _DecodeCtx, params, batch, s_max: int, low_stride: int, popc, threads: int, out, idx):
+    dev = params.device
+    runner = ctx.runner
+    F = len(batch)
+    cur: List[Optional[torch.Tensor]] = [None] * F
+    for s in range(s_max - 1, -1, -1):
+        stride = low_stride << (s_max - 1 - s)                              # doubles with every level
+        for f, (ab, low) in enumerate(batch):
+            if len(ab) - 1 == s:
+                cur[f] = low.to(torch.int32)                                # this frame's coarsest coded scale
+        act = [f for f in range(F) if cur[f] is not None]
+        if not act:
+            continue
+        seg = [0]
+        for f in act:
+            seg.append(seg[-1] + int(cur[f].shape[0]))
+        n = seg[-1]
+        fid = torch.repeat_interleave(torch.tensor(act, dtype=torch.int32, device=dev),
+                                      torch.tensor([seg[i + 1] - seg[i] for i in range(len(act))], device=dev))
+        coords = torch.cat([cur[f] for f in act], dim=0)
+        coords[:, 0] += fid * stride
+        scale = torch.full((n,), s, dtype=torch.uint8, device=dev)
+        occ = torch.zeros(n, dtype=torch.uint8, device=dev)
+        t = build_tables(coords, scale, occ, tile_ranges=False)
+        d_sym = torch.empty(n, dtype=torch.uint8, device=dev)
+        ctx.reserve(n)                                                      # pinned staging grows geometrically, reused across scales
+        streams = [unpack_bitstream(batch[f][0][s]) for f in act]
+        runner.decode_scale_batch(params, t, seg, streams, d_sym, ctx.h_cdf, ctx.h_sym, threads)
+        bits = max(1, int(F * stride * 2 - 1).bit_length())
+        child = octree_up(coords, occ, bits)                                # all frames at once: offsets double with the coordinates
+        ccount = torch.cumsum(popc[occ.long()], dim=0)
+        ends = ccount[torch.tensor([e - 1 for e in seg[1:]], device=dev)].cpu().tolist()
+        starts = [0] + [int(e) for e in ends[:-1]]
+        for i, f in enumerate(act):
+            c = child[starts[i]: int(ends[i])].clone()
+            c[:, 0] -= f * stride * 2
+            cur[f] = c
+    for f in range(F):
+        out[idx[f]] = cur[f]
+
+
 def pack_low_xyz(low_coords: Sequence[np.ndarray], mins: Sequence[np.ndarray]) -> bytes:
     """enc_all_frame_low_xyz (test_utils.py:199-232): uint8 xyz per frame, then int32 mins [F,3]."""
     parts = []

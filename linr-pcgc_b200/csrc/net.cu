@@ -1080,6 +1080,38 @@ int linr_net_decode_scale(const float *d_params, int scale_num, const linr_rows 
     return LINR_OK;
 }
 
+int linr_net_decode_scale_batch(const float *d_params, int scale_num, const linr_rows *rows, int n_seg, const int64_t *h_seg_off,
+                                const uint8_t *const *h_streams, const int64_t *h_nbytes, uint16_t *d_cdf, uint8_t *d_sym,
+                                uint16_t *h_cdf, uint8_t *h_sym, int threads, void *d_ws, size_t ws_bytes, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = check_rows(rows, scale_num, true);
+    if (rc) return rc;
+    const int64_t n = rows->n_rows;
+    if (n == 0 || n_seg <= 0) return LINR_OK;
+    LINR_REQUIRE(h_seg_off && h_streams && h_nbytes && d_cdf && d_sym && h_cdf && h_sym, "linr_net_decode_scale_batch: null buffer");
+    LINR_REQUIRE(h_seg_off[0] == 0 && h_seg_off[n_seg] == n, "linr_net_decode_scale_batch: segments must cover the rows");
+    rc = linr_net_decode_begin(d_params, scale_num, rows, d_ws, ws_bytes, stream);
+    if (rc) return rc;
+    std::vector<const uint16_t *> cdfs(n_seg);
+    std::vector<const uint8_t *> ins(n_seg);
+    std::vector<uint8_t *> syms(n_seg);
+    std::vector<int64_t> nb(n_seg), ns(n_seg);
+    for (int f = 0; f < n_seg; ++f) cdfs[f] = h_cdf + h_seg_off[f], syms[f] = h_sym + h_seg_off[f], ns[f] = h_seg_off[f + 1] - h_seg_off[f];
+    for (int k = 0; k < 8; ++k) {
+        rc = linr_net_decode_stage(d_params, scale_num, rows, k, nullptr, d_cdf, d_ws, ws_bytes, stream);
+        if (rc) return rc;
+        LINR_CHECK_CUDA(cudaMemcpyAsync(h_cdf, d_cdf, sizeof(uint16_t) * n, cudaMemcpyDeviceToHost, s));
+        LINR_CHECK_CUDA(cudaStreamSynchronize(s));
+        for (int f = 0; f < n_seg; ++f) ins[f] = h_streams[f * 8 + k], nb[f] = h_nbytes[f * 8 + k];
+        rc = linr_rc_decode_binary_batch(n_seg, cdfs.data(), ins.data(), nb.data(), syms.data(), ns.data(), threads);
+        if (rc) return rc;
+        LINR_CHECK_CUDA(cudaMemcpyAsync(d_sym, h_sym, (size_t)n, cudaMemcpyHostToDevice, s));
+        rc = linr_occ_set_stage(const_cast<uint8_t *>(rows->d_occ), d_sym, n, k, stream);
+        if (rc) return rc;
+    }
+    return LINR_OK;
+}
+
 // ---- single-layer entry points ---------------------------------------------------------------------------
 static int conv_dims_ok(int cin, int cout) { return (cin == 4 || cin == 8) && (cout == 4 || cout == 8); }
 

@@ -274,6 +274,36 @@ int linr_rc_encode_binary_batch(int n_streams, const uint16_t *const *h_cdf_mid,
     return LINR_OK;
 }
 
+int linr_rc_decode_binary_batch(int n_streams, const uint16_t *const *h_cdf_mid, const uint8_t *const *h_in, const int64_t *nbytes,
+                                uint8_t *const *h_sym, const int64_t *n, int threads) {
+    if (n_streams <= 0) return LINR_OK;
+    std::vector<int> order(n_streams);
+    for (int i = 0; i < n_streams; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return n[a] > n[b]; });  // longest first
+    std::atomic<int> next(0);
+    std::atomic<int> bad(0);
+    auto work = [&]() {
+        for (;;) {
+            const int j = next.fetch_add(1);
+            if (j >= n_streams) return;
+            const int i = order[j];
+            if (n[i] > 0 && linr_rc_decode_binary(h_cdf_mid[i], h_in[i], nbytes[i], h_sym[i], n[i]) != LINR_OK) bad.store(1);
+        }
+    };
+    int nt = threads < 1 ? 1 : threads;
+    if (nt > n_streams) nt = n_streams;
+    if (nt == 1) {
+        work();
+    } else {
+        std::vector<std::thread> pool;
+        pool.reserve(nt - 1);
+        for (int t = 0; t < nt - 1; ++t) pool.emplace_back(work);
+        work();
+        for (auto &t : pool) t.join();
+    }
+    return bad.load() ? LINR_EINVAL : LINR_OK;
+}
+
 int64_t linr_rc_encode_shared(const uint16_t *h_cdf_row, int Lp, const int16_t *h_sym, int64_t n, uint8_t *h_out, int64_t cap) {
     if (Lp < 3) return 0;
     BitWriter w(h_out, cap);

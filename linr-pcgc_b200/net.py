@@ -165,6 +165,24 @@ class NetRunner:
                                              h_cdf.data_ptr(), h_sym.data_ptr(), ptr(self.ws), self.ws.numel(), stream_ptr()),
               "linr_net_decode_scale")
 
+    def decode_scale_batch(self, params: torch.Tensor, t: RowTables, seg_off, streams, d_sym: torch.Tensor, h_cdf: torch.Tensor,
+                           h_sym: torch.Tensor, threads: int):
+        """The 8 stages of one scale for SEVERAL frames in one C call (linr_net_decode_scale_batch): t holds the frames'
+        parents concatenated (segment f = rows seg_off[f]..seg_off[f+1], kept apart in space by the caller);
+        streams[f] = the 8 stage bitstreams of frame f."""
+        n, F = t.n_rows, len(streams)
+        assert len(seg_off) == F + 1 and seg_off[0] == 0 and seg_off[-1] == n
+        assert h_cdf.is_pinned() and h_sym.is_pinned() and h_cdf.numel() >= n and h_sym.numel() >= n
+        self.reserve(n)
+        bufs = [[np.frombuffer(b, dtype=np.uint8) if len(b) else np.zeros(1, np.uint8) for b in st] for st in streams]
+        ptrs = (C.c_void_p * (8 * F))(*[b.ctypes.data for st in bufs for b in st])
+        lens = (C.c_int64 * (8 * F))(*[len(b) for st in streams for b in st])
+        offs = (C.c_int64 * (F + 1))(*[int(o) for o in seg_off])
+        rows = t.rows()
+        check(self.lib.linr_net_decode_scale_batch(ptr(params), self.S, C.byref(rows), F, offs, ptrs, lens, ptr(self.cdf), ptr(d_sym),
+                                                   h_cdf.data_ptr(), h_sym.data_ptr(), int(threads), ptr(self.ws), self.ws.numel(),
+                                                   stream_ptr()), "linr_net_decode_scale_batch")
+
     def occ_set_stage(self, occ: torch.Tensor, sym: torch.Tensor, stage: int):
         check(self.lib.linr_occ_set_stage(ptr(occ), ptr(sym), int(occ.numel()), stage, stream_ptr()), "linr_occ_set_stage")
 

@@ -111,7 +111,7 @@ def encode_gop_shared(frames: Sequence[Frame], flat_params: torch.Tensor, scale_
                       [f.point_num for f in frames])
 
 
-def decode_gop(enc: EncodedGop, device="cuda", workers: Optional[int] = None) -> List[torch.Tensor]:
+def decode_gop(enc: EncodedGop, device="cuda", workers: Optional[int] = None, batched: bool = True) -> List[torch.Tensor]:
     """decode_one_gop (decoder.py:51-147): model from its bitstream, frames coarse-to-fine; returns the original
     (min-restored) sorted coordinates of every frame as CUDA int32 [Np,3]."""
     n = P.offsets(P.param_spec(enc.scale_num))[-1]
@@ -120,7 +120,10 @@ def decode_gop(enc: EncodedGop, device="cuda", workers: Optional[int] = None) ->
     flat = model_compression.decompress_model(d, n, device)
     lows, mins = codec.unpack_low_xyz(enc.low_enc_bytes)
     jobs = [(fb, torch.from_numpy(lows[i]).to(device)) for i, fb in enumerate(enc.frame_bytes)]
-    dec = codec.decode_frames(flat, enc.scale_num, jobs, workers=workers or min(16, codec.rc.host_cores()))
+    if batched and len(jobs) >= 2:
+        dec = codec.decode_frames_batched(flat, enc.scale_num, jobs)
+    else:
+        dec = codec.decode_frames(flat, enc.scale_num, jobs, workers=workers or min(16, codec.rc.host_cores()))
     return [xyz + torch.from_numpy(mins[i].copy()).to(device) for i, xyz in enumerate(dec)]
 
 

@@ -705,3 +705,24 @@ def test_concurrent_decode_mvub_sized(L, O):
         dec = L.codec.decode_frames(flat, S, jobs, workers=workers)
         for d, f in zip(dec, frames):
             assert d.shape == f.xyz.shape and (d == f.xyz).all()
+
+
+def test_batched_lockstep_decoder_is_lossless_and_matches_per_frame_decoder(L, O):
+    """codec.decode_frames_batched: all frames of a batch decoded in lockstep (concatenated parents, one launch set and
+    one round trip per stage for the whole batch).  Same points as the per-frame decoder, with ragged scale counts
+    (a small frame stops after fewer scales), more frames than one batch, and a batch of one."""
+    pts = L.synth.make_sequence("plumbing", 5, device="cuda")
+    small = L.synth.make_sequence("tiny", 1, device="cuda")[0]
+    frames = [L.frame.prepare_frame(p, None, 64) for p in pts]
+    S = frames[0].n_scales
+    frames.insert(2, L.frame.prepare_frame(small, S, 64))        # fewer scales than the others
+    assert frames[2].n_scales < S
+    flat = O.flatten_params(O.init_params(S, seed=9), S).cuda()
+    run = L.net.NetRunner(S, max(f.tables.n_rows for f in frames), "cuda", train=False)
+    enc = L.codec.encode_frames(run, flat, frames, threads=4)
+    jobs = [(e, f.scale_coords(f.n_scales - 1).contiguous()) for f, e in zip(frames, enc)]
+    ref = L.codec.decode_frames(flat, S, jobs, workers=2)
+    for max_batch in (16, 4, 1):
+        dec = L.codec.decode_frames_batched(flat, S, jobs, max_batch=max_batch, workers=2 if max_batch > 1 else 1, threads=4)
+        for d, r, f in zip(dec, ref, frames):
+            assert d.dtype == torch.int32 and d.shape == f.xyz.shape and torch.equal(d, r) and torch.equal(d, f.xyz)
