@@ -24,7 +24,8 @@ def host_cores() -> int:
     except (AttributeError, OSError):
         aff = n
     if aff < n:
-        return max(2, aff - 1)     # the rank was bound to a slice of the cores (dist.bind_rank_cores): one stays with the launch thread
+        return max(2, aff)         # the rank was bound to a slice of the cores (dist.bind_rank_cores); while the coder runs, the
+                                   # launch thread only waits for it
     try:
         n //= max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
     except ValueError:
