@@ -535,12 +535,19 @@ void launch_bwd_w(const RowMap &m, const NetWs &w, int P, const int *w_off, cons
         kernel<<<grid, 32 * (BW3_NW + 1), smem, s>>>(a);
         return true;
     };
-    // measured (round 2, profiles/README.md): v3 wins for the 8->8 float conv (64 accumulators per lane, FMA-heavy pairs);
-    // the 4-channel and bit-input gradients do too little arithmetic per pair and stay on the lane = row kernel
-    if constexpr (CIN == 8 && COUT == 8 && MODE == 0) {
-        if (plain && dy.ld == COUT) {
+    // which classes run v3 (bit 0: 8->8, 1: 8->4, 2: 4->4, 3: bit inputs); measured choice in profiles/README.md
+    static const int v3_mask = getenv("LINR_BW3_MASK") ? atoi(getenv("LINR_BW3_MASK")) : 1;
+    constexpr int my_bit = MODE == 1 ? 8 : (CIN == 8 ? (COUT == 8 ? 1 : 2) : 4);
+    if (plain && (v3_mask & my_bit)) {
+        if (dy.ld == COUT) {
             static bool ok[64] = {false};
             if (launch3(conv27_bwd_w3_kernel<CIN, COUT, MODE, COUT>, BwdW3Cfg<CIN, COUT, MODE, COUT>::SMEM, ok)) return;
+        }
+        if constexpr (COUT == 4 && MODE == 0) {
+            if (dy.ld == 8) {
+                static bool ok[64] = {false};
+                if (launch3(conv27_bwd_w3_kernel<CIN, COUT, MODE, 8>, BwdW3Cfg<CIN, COUT, MODE, 8>::SMEM, ok)) return;
+            }
         }
     }
     using Cfg = BwdWCfg<CIN, COUT, MODE>;

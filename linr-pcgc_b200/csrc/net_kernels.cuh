@@ -796,20 +796,48 @@ __global__ void __launch_bounds__(32 * (BW3_NW + 1), 1) conv27_bwd_w3_kernel(con
     __syncthreads();
 
     if (warp == BW3_NW) {   // ---- producer warp: NST - 1 tiles ahead of the slowest consumer
-        // lane w < 14 copies the pair list of consumer warp w's slot; lane 0 also plans and copies dy and the x ranges
+        // lane w < 14 copies the pair list of consumer warp w's slot; lane 0 copies dy and the x ranges.  What a tile's
+        // copies need from global memory (its 14 list lengths, the 2 x 6 range words of its two 128-row sub-tiles) is
+        // fetched one tile ahead, so the producer never sits on a global load between two tiles.
         const int my_slot = lane < BW3_NW ? c_bw3_slot[blockIdx.x][lane] : 27;
+        const int64_t nt128 = (a.map.n_rows + 127) >> 7;
+        auto fetch = [&](int t, uint32_t &lbv, int &rv) {
+            lbv = my_slot < 27 ? (uint32_t)((a.map.pair_cnt[(tile0 + t) * 32 + my_slot] + 3) & ~3) * 4u : 0u;
+            rv = 0;
+            if constexpr (MODE != 1) {
+                if (lane < 12 && !a.no_xstage && a.map.tile_rng) {
+                    const int64_t sub = ((r0 + (int64_t)t * T) >> 7) + lane / 6;
+                    if (sub < nt128) rv = a.map.tile_rng[sub * 6 + lane % 6];
+                }
+            }
+        };
+        uint32_t lb = 0, lb_next = 0;
+        int rv = 0, rv_next = 0;
+        if (n_vt > 0) fetch(0, lb, rv);
         for (int vt = 0; vt < n_vt; ++vt) {
             const int g = vt / n_tiles, t = vt - g * n_tiles;
             const int st = vt % NST;
             const int64_t row0 = r0 + (int64_t)t * T;
             const int nrow = (int)min((int64_t)T, r1 - row0);
             unsigned char *sb = bw3_smem + st * Cfg::STAGE;
-            // global reads first (they do not touch the stage), then wait for the stage to be free
-            const uint32_t lb = my_slot < 27 ? (uint32_t)((a.map.pair_cnt[(tile0 + t) * 32 + my_slot] + 3) & ~3) * 4u : 0u;
+            if (vt + 1 < n_vt) fetch((t + 1 == n_tiles) ? 0 : t + 1, lb_next, rv_next);
+            // the three neighbour ranges of the tile, laid out back to back (every lane computes the same plan)
             StagePlan pl;
             pl.ok = false;
             if constexpr (MODE != 1) {
-                if (lane == 0 && !a.no_xstage) pl = plan_ranges(a.map.tile_rng, a.map.n_rows, row0, T, CIN, Cfg::XROWS * CIN * 4);
+                int tot = 0;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const int l0 = __shfl_sync(0xffffffffu, rv, 2 * d), h0 = __shfl_sync(0xffffffffu, rv, 2 * d + 1);
+                    const int l1 = __shfl_sync(0xffffffffu, rv, 6 + 2 * d), h1 = __shfl_sync(0xffffffffu, rv, 7 + 2 * d);
+                    int lo = INT32_MAX, hi = 0;
+                    if (h0 > l0) lo = l0, hi = h0;
+                    if (h1 > l1) lo = min(lo, l1), hi = max(hi, h1);
+                    if (hi <= lo) lo = 0, hi = 0;
+                    pl.lo[d] = lo, pl.len[d] = hi - lo, pl.base[d] = tot;
+                    tot += (pl.len[d] + 3) & ~3;
+                }
+                pl.ok = !a.no_xstage && a.map.tile_rng && tot > 0 && tot <= Cfg::XROWS;
             }
             uint32_t lsum = lb;
 #pragma unroll
@@ -825,6 +853,7 @@ __global__ void __launch_bounds__(32 * (BW3_NW + 1), 1) conv27_bwd_w3_kernel(con
             }
             __syncwarp();   // the barrier is armed before any other lane's copy can complete on it
             if (lb) bulk_g2s(sb + Cfg::DYB + Cfg::XS + lane * 1024, a.map.pair_list + ((tile0 + t) * 27 + my_slot) * 256, lb, &full[st]);
+            lb = lb_next, rv = rv_next;
         }
         return;
     }
