@@ -736,35 +736,26 @@ struct BwdW3Cfg {
     static_assert(STAGE % 128 == 0, "stages keep the 128-byte alignment of the bank swizzle");
 };
 
-// One staged row as raw 16-byte pieces.  8-channel rows are 32 bytes: eight consecutive rows would hit only four of
-// the eight 16-byte bank groups with their first halves, so rows 4..7 of every eight read their halves in the
-// opposite order (conflict-free for consecutive rows; resolved with two selects per half) ...
+// One staged row as raw 16-byte pieces.  8-channel rows are 32 bytes: eight lanes reading the first halves of eight
+// consecutive rows would hit only four of the eight 16-byte bank groups.  So the ORDER of a lane's two loads depends on
+// the lane: lanes with bit 2 set read the upper half first (b0 / b1 are the row base plus the half the lane reads
+// first / second).  A quarter warp then covers all eight bank groups when its rows are consecutive, and because the
+// order is a constant of the lane nothing is selected per row: the lane's sums are simply kept in its own channel
+// order (channel c of the lane = channel c ^ 4 of the row for those lanes) and put right once, in flush().
 template <int C>
 struct RawRow {
     float4 u[C / 4];
-    int sw;
 };
 template <int C>
-__device__ __forceinline__ void raw_load(const float *base, int p, int ld, RawRow<C> &r) {
-    const float *q = base + p * ld;
-    if constexpr (C == 8) {
-        r.sw = (p >> 2) & 1;
-        r.u[0] = *reinterpret_cast<const float4 *>(q + 4 * r.sw);
-        r.u[1] = *reinterpret_cast<const float4 *>(q + 4 * (r.sw ^ 1));
-    } else {
-        r.sw = 0;
-        r.u[0] = *reinterpret_cast<const float4 *>(q);
-    }
+__device__ __forceinline__ void raw_load(const float *b0, const float *b1, int p, int ld, RawRow<C> &r) {
+    r.u[0] = *reinterpret_cast<const float4 *>(b0 + p * ld);
+    if constexpr (C == 8) r.u[1] = *reinterpret_cast<const float4 *>(b1 + p * ld);
 }
-// ... and in channel order
+// ... as floats, in the lane's channel order
 template <int C>
 __device__ __forceinline__ void raw_resolve(const RawRow<C> &r, float (&v)[C]) {
-    if constexpr (C == 8) {
-        const float4 lo = r.sw ? r.u[1] : r.u[0], hi = r.sw ? r.u[0] : r.u[1];
-        v[0] = lo.x, v[1] = lo.y, v[2] = lo.z, v[3] = lo.w, v[4] = hi.x, v[5] = hi.y, v[6] = hi.z, v[7] = hi.w;
-    } else {
-        v[0] = r.u[0].x, v[1] = r.u[0].y, v[2] = r.u[0].z, v[3] = r.u[0].w;
-    }
+    v[0] = r.u[0].x, v[1] = r.u[0].y, v[2] = r.u[0].z, v[3] = r.u[0].w;
+    if constexpr (C == 8) v[4] = r.u[1].x, v[5] = r.u[1].y, v[6] = r.u[1].z, v[7] = r.u[1].w;
 }
 
 template <int CIN, int COUT, int MODE, int DLD>
@@ -862,6 +853,9 @@ __global__ void __launch_bounds__(32 * (BW3_NW + 1), 1) conv27_bwd_w3_kernel(con
     float *out = a.partial + blockIdx.y * a.P;
     const bool is_bias = slot == 27;
     const int dxi = slot % 3;   // offset k = slot = c + 9 j, dx index = c % 3 = k % 3
+    const int hs = (lane >> 2) & 1;                          // which half of a 32-byte row this lane reads first
+    const int dh0 = (COUT == 8) ? 4 * hs : 0, dh1 = (COUT == 8) ? 4 * (hs ^ 1) : 0;
+    const int xh0 = (XW == 8) ? 4 * hs : 0, xh1 = (XW == 8) ? 4 * (hs ^ 1) : 0;
     u64 acc[CI][HQ];
 #pragma unroll
     for (int i = 0; i < CI; ++i)
@@ -883,6 +877,12 @@ __global__ void __launch_bounds__(32 * (BW3_NW + 1), 1) conv27_bwd_w3_kernel(con
             for (int q = 0; q < HQ; ++q) ffma2_acc(acc[i][q], xx, db[q]);
         }
     };
+    // the sum for (input channel i, output channel pair q) out of the lane's own channel order (see RawRow)
+    auto lane_order = [&](int i, int q) -> u64 {
+        constexpr int IX = (XW == 8) ? 4 : 0, QX = (COUT == 8) ? 2 : 0;
+        if constexpr (IX == 0 && QX == 0) return acc[i][q];
+        else return hs ? acc[i ^ IX][q ^ QX] : acc[i][q];
+    };
     // end of a group's pass over the chunk: reduce the lane-private sums, store the partial, start over
     auto flush = [&](int g) {
         const int cin = (MODE == 1) ? (a.cin_base + g * a.cin_step) : CIN;
@@ -890,7 +890,7 @@ __global__ void __launch_bounds__(32 * (BW3_NW + 1), 1) conv27_bwd_w3_kernel(con
             if (a.b_off[g] >= 0) {
                 float v[COUT];
 #pragma unroll
-                for (int q = 0; q < HQ; ++q) unpack2(acc[0][q], v[2 * q], v[2 * q + 1]);
+                for (int q = 0; q < HQ; ++q) unpack2((COUT == 8 && hs) ? acc[0][q ^ (HQ / 2)] : acc[0][q], v[2 * q], v[2 * q + 1]);
 #pragma unroll
                 for (int co = 0; co < COUT; ++co) {
 #pragma unroll
@@ -908,7 +908,7 @@ __global__ void __launch_bounds__(32 * (BW3_NW + 1), 1) conv27_bwd_w3_kernel(con
 #pragma unroll
             for (int i = 0; i < CI; ++i)
 #pragma unroll
-                for (int q = 0; q < HQ; ++q) unpack2(acc[i][q], v[i * COUT + 2 * q], v[i * COUT + 2 * q + 1]);
+                for (int q = 0; q < HQ; ++q) unpack2(lane_order(i, q), v[i * COUT + 2 * q], v[i * COUT + 2 * q + 1]);
             warp_transpose_reduce<VP>(v, lane);
 #pragma unroll
             for (int i = 0; i < VP / 32; ++i) {
@@ -946,7 +946,7 @@ __global__ void __launch_bounds__(32 * (BW3_NW + 1), 1) conv27_bwd_w3_kernel(con
             for (int rl = lane; rl < nrow; rl += 32) {
                 RawRow<COUT> rr;
                 float d[COUT];
-                raw_load<COUT>(sdy, rl, DLD, rr);
+                raw_load<COUT>(sdy + dh0, sdy + dh1, rl, DLD, rr);
                 raw_resolve<COUT>(rr, d);
 #pragma unroll
                 for (int q = 0; q < HQ; ++q) fadd2_acc(acc[0][q], pack2(d[2 * q], d[2 * q + 1]));
@@ -956,7 +956,8 @@ __global__ void __launch_bounds__(32 * (BW3_NW + 1), 1) conv27_bwd_w3_kernel(con
             // Software pipeline: the rows of batch b+1 are loaded before the FMAs of batch b.
             const uint32_t *lst = reinterpret_cast<const uint32_t *>(sb + Cfg::DYB + Cfg::XS) + warp * 256;
             const int dlt = s_plan[st][dxi];
-            const float *sx = reinterpret_cast<const float *>(sb + Cfg::DYB);
+            const float *sx0 = reinterpret_cast<const float *>(sb + Cfg::DYB) + xh0, *sx1 = reinterpret_cast<const float *>(sb + Cfg::DYB) + xh1;
+            const float *sdy0 = sdy + dh0, *sdy1 = sdy + dh1;
             RawRow<COUT> rd;
             RawRow<(MODE == 1) ? 4 : CIN> rx;
             unsigned ob = 0;
@@ -964,12 +965,12 @@ __global__ void __launch_bounds__(32 * (BW3_NW + 1), 1) conv27_bwd_w3_kernel(con
                 const bool on = b + lane < cnt;
                 const uint32_t e = on ? lst[b + lane] : 0u;
                 const int o = on ? (int)(e >> 24) : T;
-                raw_load<COUT>(sdy, o, DLD, rd);
+                raw_load<COUT>(sdy0, sdy1, o, DLD, rd);
                 if constexpr (MODE == 1) {
                     ob = on ? (unsigned)a.occ[e & 0xffffffu] : 0u;
                 } else {
                     const int n = on ? (int)(e & 0xffffffu) + dlt : Cfg::XROWS;
-                    raw_load<CIN>(sx, n, CIN, rx);
+                    raw_load<CIN>(sx0, sx1, n, CIN, rx);
                 }
             };
             if (cnt > 0) load_batch(0);
@@ -992,12 +993,18 @@ __global__ void __launch_bounds__(32 * (BW3_NW + 1), 1) conv27_bwd_w3_kernel(con
                 const uint32_t e = on ? lst[b + lane] : 0u;
                 float d[COUT], xb[XW];
                 RawRow<COUT> rd;
-                raw_load<COUT>(sdy, on ? (int)(e >> 24) : T, DLD, rd);
+                raw_load<COUT>(sdy + dh0, sdy + dh1, on ? (int)(e >> 24) : T, DLD, rd);
                 raw_resolve<COUT>(rd, d);
 #pragma unroll
                 for (int i = 0; i < XW; ++i) xb[i] = 0.f;
                 if constexpr (MODE != 1) {
-                    if (on) gather_row<CIN>(xg + (int64_t)(e & 0xffffffu) * CIN, xb);
+                    if (on) {   // the two halves in the lane's order, like the staged rows
+                        const float *xr = xg + (int64_t)(e & 0xffffffu) * CIN;
+                        RawRow<CIN> rx;
+                        rx.u[0] = __ldg(reinterpret_cast<const float4 *>(xr + xh0));
+                        if constexpr (CIN == 8) rx.u[1] = __ldg(reinterpret_cast<const float4 *>(xr + xh1));
+                        raw_resolve<CIN>(rx, xb);
+                    }
                 }
                 fma_pair(d, xb);
             }
