@@ -536,7 +536,7 @@ void launch_bwd_w(const RowMap &m, const NetWs &w, int P, const int *w_off, cons
         return true;
     };
     // which classes run v3 (bit 0: 8->8, 1: 8->4, 2: 4->4, 3: bit inputs); measured choice in profiles/README.md
-    static const int v3_mask = getenv("LINR_BW3_MASK") ? atoi(getenv("LINR_BW3_MASK")) : 1;
+    static const int v3_mask = getenv("LINR_BW3_MASK") ? atoi(getenv("LINR_BW3_MASK")) : 11;   // 4->4 stays on the lane = row kernel
     constexpr int my_bit = MODE == 1 ? 8 : (CIN == 8 ? (COUT == 8 ? 1 : 2) : 4);
     if (plain && (v3_mask & my_bit)) {
         if (dy.ld == COUT) {

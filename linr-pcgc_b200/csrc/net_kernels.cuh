@@ -954,23 +954,30 @@ __global__ void __launch_bounds__(32 * (BW3_NW + 1), 1) conv27_bwd_w3_kernel(con
         } else if ((MODE == 1) || s_plan[st][3]) {
             // every operand in shared memory (MODE 1: the neighbour's occupancy byte comes from global memory).
             // Software pipeline: the rows of batch b+1 are loaded before the FMAs of batch b.
-            const uint32_t *lst = reinterpret_cast<const uint32_t *>(sb + Cfg::DYB + Cfg::XS) + warp * 256;
+            // Addresses are 32-bit shared-window byte offsets; the per-tile terms (stage, the lane's halves, the shift of
+            // the offset's neighbour range) are folded into four bases, so a pair costs a shift/mask and an add per row.
+            constexpr int DSH = (DLD == 8) ? 5 : 4, XSH = (CIN == 8) ? 5 : 4;
             const int dlt = s_plan[st][dxi];
-            const float *sx0 = reinterpret_cast<const float *>(sb + Cfg::DYB) + xh0, *sx1 = reinterpret_cast<const float *>(sb + Cfg::DYB) + xh1;
-            const float *sdy0 = sdy + dh0, *sdy1 = sdy + dh1;
+            const uint32_t a_l = smem_u32(sb + Cfg::DYB + Cfg::XS) + (uint32_t)(warp * 256 + lane) * 4u;
+            const uint32_t a_d0 = smem_u32(sdy) + dh0 * 4u, a_d1 = smem_u32(sdy) + dh1 * 4u;
+            const uint32_t a_x = smem_u32(sb + Cfg::DYB) + ((uint32_t)dlt << XSH);
+            const uint32_t a_x0 = a_x + xh0 * 4u, a_x1 = a_x + xh1 * 4u;
+            const uint32_t null_x = (uint32_t)(Cfg::XROWS - dlt) << XSH;   // the zero row, for idle lanes of the last batch
             RawRow<COUT> rd;
             RawRow<(MODE == 1) ? 4 : CIN> rx;
             unsigned ob = 0;
             auto load_batch = [&](int b) {
                 const bool on = b + lane < cnt;
-                const uint32_t e = on ? lst[b + lane] : 0u;
-                const int o = on ? (int)(e >> 24) : T;
-                raw_load<COUT>(sdy0, sdy1, o, DLD, rd);
+                const uint32_t e = lds_u32(a_l + (uint32_t)b * 4u);   // inside the warp's own 256-entry slot either way
+                const uint32_t od = on ? ((e >> (24 - DSH)) & (0xffu << DSH)) : ((uint32_t)T << DSH);
+                rd.u[0] = lds_f4(a_d0 + od);
+                if constexpr (COUT == 8) rd.u[1] = lds_f4(a_d1 + od);
                 if constexpr (MODE == 1) {
                     ob = on ? (unsigned)a.occ[e & 0xffffffu] : 0u;
                 } else {
-                    const int n = on ? (int)(e & 0xffffffu) + dlt : Cfg::XROWS;
-                    raw_load<CIN>(sx0, sx1, n, CIN, rx);
+                    const uint32_t xo = on ? ((e & 0xffffffu) << XSH) : null_x;
+                    rx.u[0] = lds_f4(a_x0 + xo);
+                    if constexpr (CIN == 8) rx.u[1] = lds_f4(a_x1 + xo);
                 }
             };
             if (cnt > 0) load_batch(0);
