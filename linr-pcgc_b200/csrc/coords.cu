@@ -251,15 +251,24 @@ __global__ void __launch_bounds__(128) tile_range_kernel(const int32_t *__restri
     }
 }
 
-// Pair lists: for every 256-row tile and every kernel offset k the (output row, neighbour row) pairs that exist, in
-// row order: entry = (row - tile_base) << 24 | neighbour_row.  One warp per (tile, column c) fills the three lists of
-// its column (k = c + 9 j) by ballot compaction, so a list is a deterministic function of the kernel map.  Lists have
-// a fixed capacity of 256 entries (list t,k starts at (t * 27 + k) * 256); cnt[t * 32 + k] entries are valid.
-// The conv and weight-gradient kernels walk these lists 32 pairs at a time: no lane ever multiplies by the zero of
-// an absent neighbour (14.3 of 27 offsets are occupied on a surface).
+// Pair lists: for every 256-row tile and every kernel offset k the (output row, neighbour row) pairs that exist:
+// entry = (row - tile_base) << 24 | neighbour_row.  Lists have a fixed capacity of 256 entries (list t,k starts at
+// (t * 27 + k) * 256); cnt[t * 32 + k] entries are valid.  The weight-gradient kernel walks a list 32 pairs at a time,
+// one pair per lane, and reads both rows (32 bytes each) from shared memory with two 16-byte loads per row.  A quarter
+// warp of such loads is conflict-free when each aligned group of FOUR lanes holds rows that differ modulo 4 (lanes
+// 0..3 of a quarter read one half of their rows, lanes 4..7 the other, see RawRow in net_kernels.cuh).  In row order
+// the rows of a list have gaps and 1.63 x the ideal number of wavefronts; so the ORDER inside a list is chosen here,
+// once per frame: entries are classed by (row mod 4, neighbour mod 4); every cyclic diagonal
+// {(a, a + d mod 4), a = 0..3} yields min-count groups of four entries with distinct rows AND distinct neighbours
+// (neighbour - row is constant along a column run, so most entries sit on one diagonal); what is left over follows in
+// row order.  1.2 x ideal for both operands.  One warp per (tile, column c) builds the three lists of its column
+// (k = c + 9 j) with ballots only, so a list is a deterministic function of the kernel map.
 __global__ void __launch_bounds__(288) pair_list_kernel(const int32_t *__restrict__ anchor, int64_t ld, const uint32_t *__restrict__ mask,
                                                         int64_t n, int32_t *__restrict__ cnt, uint32_t *__restrict__ list) {
+    __shared__ uint32_t s_asc[9][3][256];   // the lists in row order
+    __shared__ uint8_t s_rank[9][256];      // rank of an entry inside its class
     const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;   // 9 warps: one per (dx,dy) column
+    const uint32_t lt = (1u << lane) - 1u;
     const int64_t tile = blockIdx.x, base = tile * 256;
     int count[3] = {0, 0, 0};
     for (int st = 0; st < 8; ++st) {
@@ -277,11 +286,63 @@ __global__ void __launch_bounds__(288) pair_list_kernel(const int32_t *__restric
             const uint32_t bal = __ballot_sync(0xffffffffu, has);
             if (has) {
                 const int nb = an + __popc(m3 & ((1u << j) - 1u));
-                const int pos = count[j] + __popc(bal & ((1u << lane) - 1u));
-                list[(tile * 27 + (c + 9 * j)) * 256 + pos] = ((uint32_t)rl << 24) | (uint32_t)nb;
+                s_asc[c][j][count[j] + __popc(bal & lt)] = ((uint32_t)rl << 24) | (uint32_t)nb;
             }
             count[j] += __popc(bal);
         }
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int j = 0; j < 3; ++j) {
+        const int nj = count[j];
+        const uint32_t *asc = s_asc[c][j];
+        uint32_t *out = list + (tile * 27 + (c + 9 * j)) * 256;
+        // pass 1: class counts (warp-uniform registers) and the rank of every entry inside its class
+        int ncls[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) ncls[q] = 0;
+        for (int i0 = 0; i0 < nj; i0 += 32) {
+            const bool on = i0 + lane < nj;
+            const uint32_t e = on ? asc[i0 + lane] : 0u;
+            const int cls = on ? (int)(((e >> 24) & 3u) * 4u + (e & 3u)) : -1;
+            int rk = 0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const uint32_t bal = __ballot_sync(0xffffffffu, cls == q);
+                if (cls == q) rk = ncls[q] + __popc(bal & lt);
+                ncls[q] += __popc(bal);
+            }
+            if (on) s_rank[c][i0 + lane] = (uint8_t)rk;   // < 256: a class with 256 entries would need 1024 rows
+        }
+        // groups of four per diagonal d: g[d] = min over a of count(a, a + d); diagonals laid out one after the other
+        int g[4], gb[5];
+        gb[0] = 0;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            g[d] = 256;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) g[d] = min(g[d], ncls[a * 4 + ((a + d) & 3)]);
+            gb[d + 1] = gb[d] + g[d];
+        }
+        __syncwarp();
+        // pass 2: grouped entries to their slot, the rest behind them in row order
+        int tail = 4 * gb[4];
+        for (int i0 = 0; i0 < nj; i0 += 32) {
+            const bool on = i0 + lane < nj;
+            const uint32_t e = on ? asc[i0 + lane] : 0u;
+            const int a = (int)((e >> 24) & 3u), d = (int)((e - (e >> 24)) & 3u);
+            const int rk = on ? (int)s_rank[c][i0 + lane] : 0;
+            int gd = g[0], gbd = gb[0];
+#pragma unroll
+            for (int q = 1; q < 4; ++q)
+                if (d == q) gd = g[q], gbd = gb[q];
+            const bool grouped = on && rk < gd;
+            const uint32_t rest = __ballot_sync(0xffffffffu, on && !grouped);
+            if (grouped) out[4 * (gbd + rk) + a] = e;
+            else if (on) out[tail + __popc(rest & lt)] = e;
+            tail += __popc(rest);
+        }
+        __syncwarp();
     }
     if (lane < 3) cnt[tile * 32 + c + 9 * lane] = lane == 0 ? count[0] : (lane == 1 ? count[1] : count[2]);
     if (c == 0 && lane >= 27) cnt[tile * 32 + lane] = 0;

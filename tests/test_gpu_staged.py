@@ -45,9 +45,34 @@ def test_tile_ranges_bit_exact(L, name):
     np.testing.assert_array_equal(t.tile_rng.cpu().numpy(), _ranges_from_dense(nb, t.n_rows))
 
 
+def _pair_order(rl, nbv):
+    """Order of the entries inside a pair list (coords.cu pair_list_kernel): entries are classed by (row mod 4, neighbour
+    mod 4); diagonal d = (neighbour - row) mod 4 gives g[d] = min class count groups of four entries with distinct rows and
+    distinct neighbours modulo 4 (the shared-memory bank condition of the weight-gradient kernel), diagonals one after
+    the other; what is left follows in row order.  Returns the permutation and the number of grouped entries."""
+    a, b = rl & 3, nbv & 3
+    d = (b - a) & 3
+    rank = np.zeros(len(rl), np.int64)
+    ncls = np.zeros((4, 4), np.int64)
+    for i in range(len(rl)):
+        rank[i] = ncls[a[i], b[i]]
+        ncls[a[i], b[i]] += 1
+    g = [min(ncls[x, (x + dd) & 3] for x in range(4)) for dd in range(4)]
+    gb = np.concatenate([[0], np.cumsum(g)])
+    head = np.full(4 * gb[4], -1, np.int64)
+    tail = []
+    for i in range(len(rl)):
+        if rank[i] < g[d[i]]:
+            head[4 * (gb[d[i]] + rank[i]) + a[i]] = i
+        else:
+            tail.append(i)
+    return np.concatenate([head, np.array(tail, np.int64)]).astype(np.int64), int(4 * gb[4])
+
+
 @pytest.mark.parametrize("name", ["tiny", "ragged", "mid"])
 def test_pair_lists_bit_exact(L, name):
-    """linr_pair_lists: list (t,k) = rows of tile t with a neighbour at offset k, in row order, with that neighbour."""
+    """linr_pair_lists: list (t,k) = the rows of tile t with a neighbour at offset k and that neighbour, in the
+    bank-conflict-avoiding order of _pair_order."""
     g = _load(f"int_{name}.npz")
     fr = L.frame.prepare_frame(_cuda(g["points"]), None, 64)
     t = fr.tables
@@ -56,14 +81,22 @@ def test_pair_lists_bit_exact(L, name):
     cnt = t.pair_cnt.cpu().numpy()
     lst = t.pair_list.cpu().numpy().view(np.uint32)
     assert cnt.shape == ((n + 255) // 256, 32) and lst.shape == ((n + 255) // 256, 27, 256)
+    grouped = total = 0
     for ti in range(cnt.shape[0]):
         blk = nb[ti * 256:(ti + 1) * 256]
         for k in range(27):
             rl = np.nonzero(blk[:, k] >= 0)[0]
             assert cnt[ti, k] == len(rl)
-            want = (rl.astype(np.uint32) << np.uint32(24)) | blk[rl, k].astype(np.uint32)
+            perm, nh = _pair_order(rl, blk[rl, k])
+            want = (rl[perm].astype(np.uint32) << np.uint32(24)) | blk[rl[perm], k].astype(np.uint32)
             np.testing.assert_array_equal(lst[ti, k, :len(rl)], want)
+            got = lst[ti, k, :nh].reshape(-1, 4)
+            assert (np.sort((got >> np.uint32(24)) & 3, axis=1) == np.arange(4)).all()     # rows distinct modulo 4
+            assert (np.sort(got & np.uint32(3), axis=1) == np.arange(4)).all()             # neighbours too
+            grouped, total = grouped + nh, total + len(rl)
         assert (cnt[ti, 27:] == 0).all()
+    if name == "mid":
+        assert grouped >= 0.6 * total
 
 
 def _frames(L):
