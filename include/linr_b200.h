@@ -153,8 +153,9 @@ typedef struct {
                                 * inputs in shared memory with bulk (TMA) copies; without it they gather through L1.  Same
                                 * results bit for bit either way.  When set, d_mask must be readable up to `ld` entries. */
     const int32_t *d_pair_cnt;   /* [ceil(n_rows/256),32] and */
-    const uint32_t *d_pair_list; /* [ceil(n_rows/256),27,256] from linr_pair_lists, or NULL: per 256-row tile and kernel offset
-                                  * the existing (row, neighbour) pairs.  With them the kernels only touch occupied offsets. */
+    const uint32_t *d_pair_list; /* [ceil(n_rows/256),27*256] from linr_pair_lists, or NULL: per 256-row tile and kernel offset
+                                  * the existing (row, neighbour) pairs.  With them the weight-gradient kernel only touches
+                                  * occupied offsets. */
 } linr_rows;
 
 /* Neighbour row ranges per 128-row tile (see linr_rows.d_tile_rng); d_rng int32 [ceil(n_rows/128), 6] =
@@ -162,9 +163,16 @@ typedef struct {
 int linr_tile_ranges(const linr_rows *rows, int32_t *d_rng, void *stream);
 
 /* Pair lists of the kernel map (see linr_rows.d_pair_cnt / d_pair_list): list (t,k) holds the rows of 256-row tile t that
- * have a neighbour at offset k, in row order, as (row - 256 t) << 24 | neighbour_row; d_cnt[t*32 + k] of its 256 slots are
- * valid.  Same information as ME's per-offset in/out kernel maps, tiled.  n_rows < 2^24. */
+ * have a neighbour at offset k as (row - 256 t) << 24 | neighbour_row; d_cnt[t*32 + k] is its length.  Same information
+ * as ME's per-offset in/out kernel maps, tiled.  n_rows < 2^24.
+ * Layout (made for the weight-gradient kernel, which fetches half of a tile's lists with one bulk copy and reads pairs
+ * 32 at a time from shared memory): the 27 offsets are dealt to two halves, order28 = 2 x 14 offsets from
+ * linr_pair_list_order (27 = no list); the lists of half h lie back to back from entry h*14*256 of the tile's 27*256
+ * entries, in that order, each starting on a multiple of 4 entries.  Inside a list, aligned groups of four entries have
+ * rows AND neighbours that differ modulo 4 wherever the kernel map allows it (bank-conflict-free 16-byte loads), the
+ * remaining entries follow in row order. */
 int linr_pair_lists(const linr_rows *rows, int32_t *d_cnt, uint32_t *d_list, void *stream);
+void linr_pair_list_order(int32_t *order28);
 
 /* Workspace sizes (bytes) for n_rows rows. `train`!=0 includes saved activations and gradients. */
 size_t linr_net_ws_bytes(int64_t n_rows, int train);

@@ -53,6 +53,7 @@ SIGNATURES = {
     "linr_nbr_build": (_I, [_P, _P, _I64, _P, _I64, _P, _P, _I64, _P, _P, _P]),
     "linr_tile_ranges": (_I, [_RP, _P, _P]),
     "linr_pair_lists": (_I, [_RP, _P, _P, _P]),
+    "linr_pair_list_order": (None, [_P]),
     "linr_hash_lookup": (_I, [_P, _P, _I64, _P, _I64, _P, _P]),
     "linr_param_count": (_I64, [_I]),
     "linr_param_offsets": (_I, [_I, C.POINTER(_I64), _I]),

@@ -47,3 +47,14 @@ struct WsCursor {
 };
 
 int linr_sm_count();
+
+// Weight-gradient v3 (net_kernels.cuh) and the pair lists it walks (coords.cu): the 27 offsets + the bias are dealt to
+// two halves of 14 slots (27 = bias, no list); a block works on one half, warp i of the block on slot [half][i].  The
+// table balances the offsets' densities (centre 1.0, faces .65, edges .51, corners .41) per SM sub-partition.  The
+// pair lists of a tile are stored half by half in this order, so that a block fetches its 14 lists with ONE bulk copy.
+#define LINR_BW3_SLOTS                                                                             \
+    {                                                                                              \
+        {1, 5, 12, 10, 3, 7, 14, 16, 0, 6, 9, 11, 2, 8}, { 15, 19, 4, 13, 17, 21, 22, 24, 18, 23, 25, 26, 20, 27 } \
+    }
+constexpr int BW3_NW = 14, BW3_T = 256;
+constexpr int PAIR_TILE_ENTRIES = 27 * 256, PAIR_HALF_ENTRIES = BW3_NW * 256;   // list storage of a tile / where half 1 starts

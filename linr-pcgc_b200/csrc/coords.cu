@@ -252,8 +252,10 @@ __global__ void __launch_bounds__(128) tile_range_kernel(const int32_t *__restri
 }
 
 // Pair lists: for every 256-row tile and every kernel offset k the (output row, neighbour row) pairs that exist:
-// entry = (row - tile_base) << 24 | neighbour_row.  Lists have a fixed capacity of 256 entries (list t,k starts at
-// (t * 27 + k) * 256); cnt[t * 32 + k] entries are valid.  The weight-gradient kernel walks a list 32 pairs at a time,
+// entry = (row - tile_base) << 24 | neighbour_row; cnt[t * 32 + k] entries.  Storage: 27 * 256 entries per tile; the
+// lists of the offsets of half h (LINR_BW3_SLOTS, common.cuh) lie back to back from entry h * 14 * 256 of the tile's
+// storage, in table order, every list starting on a multiple of 4 entries -- what one block of the weight-gradient
+// kernel needs of a tile is ONE contiguous run.  That kernel walks a list 32 pairs at a time,
 // one pair per lane, and reads both rows (32 bytes each) from shared memory with two 16-byte loads per row.  A quarter
 // warp of such loads is conflict-free when each aligned group of FOUR lanes holds rows that differ modulo 4 (lanes
 // 0..3 of a quarter read one half of their rows, lanes 4..7 the other, see RawRow in net_kernels.cuh).  In row order
@@ -263,10 +265,24 @@ __global__ void __launch_bounds__(128) tile_range_kernel(const int32_t *__restri
 // (neighbour - row is constant along a column run, so most entries sit on one diagonal); what is left over follows in
 // row order.  1.2 x ideal for both operands.  One warp per (tile, column c) builds the three lists of its column
 // (k = c + 9 j) with ballots only, so a list is a deterministic function of the kernel map.
+__constant__ int8_t c_pair_slot[2][BW3_NW] = LINR_BW3_SLOTS;
+struct PairPos {
+    int8_t v[27];   // half << 4 | index inside the half, of offset k
+};
+constexpr PairPos make_pair_pos() {
+    constexpr int8_t t[2][BW3_NW] = LINR_BW3_SLOTS;
+    PairPos p{};
+    for (int h = 0; h < 2; ++h)
+        for (int i = 0; i < BW3_NW; ++i)
+            if (t[h][i] < 27) p.v[t[h][i]] = (int8_t)(h << 4 | i);
+    return p;
+}
+__constant__ PairPos c_pair_pos_tab = make_pair_pos();
 __global__ void __launch_bounds__(288) pair_list_kernel(const int32_t *__restrict__ anchor, int64_t ld, const uint32_t *__restrict__ mask,
                                                         int64_t n, int32_t *__restrict__ cnt, uint32_t *__restrict__ list) {
     __shared__ uint32_t s_asc[9][3][256];   // the lists in row order
     __shared__ uint8_t s_rank[9][256];      // rank of an entry inside its class
+    __shared__ int s_cnt[27];
     const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;   // 9 warps: one per (dx,dy) column
     const uint32_t lt = (1u << lane) - 1u;
     const int64_t tile = blockIdx.x, base = tile * 256;
@@ -291,12 +307,19 @@ __global__ void __launch_bounds__(288) pair_list_kernel(const int32_t *__restric
             count[j] += __popc(bal);
         }
     }
-    __syncwarp();
+    if (lane < 3) s_cnt[c + 9 * lane] = lane == 0 ? count[0] : (lane == 1 ? count[1] : count[2]);
+    __syncthreads();
 #pragma unroll 1
     for (int j = 0; j < 3; ++j) {
         const int nj = count[j];
         const uint32_t *asc = s_asc[c][j];
-        uint32_t *out = list + (tile * 27 + (c + 9 * j)) * 256;
+        // where list k starts: after the lists that precede it in its half (each rounded up to 4 entries)
+        const int k = c + 9 * j, half = c_pair_pos_tab.v[k] >> 4, idx = c_pair_pos_tab.v[k] & 15;
+        int before = (lane < idx) ? ((s_cnt[c_pair_slot[half][lane]] + 3) & ~3) : 0;
+#pragma unroll
+        for (int o = 8; o; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+        before = __shfl_sync(0xffffffffu, before, 0);
+        uint32_t *out = list + tile * PAIR_TILE_ENTRIES + half * PAIR_HALF_ENTRIES + before;
         // pass 1: class counts (warp-uniform registers) and the rank of every entry inside its class
         int ncls[16];
 #pragma unroll
@@ -550,6 +573,12 @@ int linr_tile_ranges(const linr_rows *rows, int32_t *d_rng, void *stream) {
     }
     LINR_LAUNCH_CHECK();
     return LINR_OK;
+}
+
+void linr_pair_list_order(int32_t *order28) {
+    constexpr int8_t t[2][BW3_NW] = LINR_BW3_SLOTS;
+    for (int h = 0; h < 2; ++h)
+        for (int i = 0; i < BW3_NW; ++i) order28[h * BW3_NW + i] = t[h][i];
 }
 
 int linr_pair_lists(const linr_rows *rows, int32_t *d_cnt, uint32_t *d_list, void *stream) {

@@ -716,10 +716,7 @@ __global__ void __launch_bounds__(BwdWCfg<CIN, COUT, MODE>::TPB) __maxnreg__((Bw
 //  * lane-private dW[k] (CI x COUT, packed FFMA2) over the warp's pairs, transposing butterfly at the end of the chunk,
 //    one partial per (chunk, offset): fixed order, no floating-point atomics -> bitwise reproducible run to run.
 // ------------------------------------------------------------------------------------------------
-constexpr int BW3_NW = 14, BW3_T = 256;
-__constant__ int8_t c_bw3_slot[2][BW3_NW] = {
-    {1, 5, 12, 10, 3, 7, 14, 16, 0, 6, 9, 11, 2, 8},
-    {15, 19, 4, 13, 17, 21, 22, 24, 18, 23, 25, 26, 20, 27}};
+__constant__ int8_t c_bw3_slot[2][BW3_NW] = LINR_BW3_SLOTS;   // common.cuh
 
 // DLD: row stride of dy in floats (COUT, or 8 when a 4-channel slice of an 8-wide tensor is the gradient)
 template <int CIN, int COUT, int MODE, int DLD>
@@ -764,7 +761,7 @@ __global__ void __launch_bounds__(32 * (BW3_NW + 1), 1) conv27_bwd_w3_kernel(con
     constexpr int CI = Cfg::CI, HQ = COUT / 2, V = Cfg::V, VP = Cfg::VP, T = BW3_T, NST = Cfg::NST;
     constexpr int XW = (MODE == 1) ? 1 : CIN;
     extern __shared__ __align__(128) unsigned char bw3_smem[];
-    __shared__ int s_plan[NST][4];
+    __shared__ int s_plan[NST][4 + BW3_NW + 2];   // x-range shifts, staged flag, byte offset of every warp's list
     uint64_t *full = reinterpret_cast<uint64_t *>(bw3_smem + NST * Cfg::STAGE), *empty = full + NST;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t r0 = blockIdx.y * a.chunk;   // chunks are whole 256-row tiles
@@ -787,9 +784,10 @@ __global__ void __launch_bounds__(32 * (BW3_NW + 1), 1) conv27_bwd_w3_kernel(con
     __syncthreads();
 
     if (warp == BW3_NW) {   // ---- producer warp: NST - 1 tiles ahead of the slowest consumer
-        // lane w < 14 copies the pair list of consumer warp w's slot; lane 0 copies dy and the x ranges.  What a tile's
-        // copies need from global memory (its 14 list lengths, the 2 x 6 range words of its two 128-row sub-tiles) is
-        // fetched one tile ahead, so the producer never sits on a global load between two tiles.
+        // Lane 0 issues the (at most) five bulk copies of a tile: dy rows, the block's 14 pair lists (contiguous in global
+        // memory, coords.cu) and the three x ranges -- a bulk copy costs its issuing warp ~170 cycles, and with one copy
+        // per list (18 per tile) the producer was the pace of the whole kernel.  What the copies need from global memory
+        // (the 14 list lengths, the 2 x 6 range words of the tile's two 128-row sub-tiles) is fetched one tile ahead.
         const int my_slot = lane < BW3_NW ? c_bw3_slot[blockIdx.x][lane] : 27;
         const int64_t nt128 = (a.map.n_rows + 127) >> 7;
         auto fetch = [&](int t, uint32_t &lbv, int &rv) {
@@ -830,20 +828,26 @@ __global__ void __launch_bounds__(32 * (BW3_NW + 1), 1) conv27_bwd_w3_kernel(con
                 }
                 pl.ok = !a.no_xstage && a.map.tile_rng && tot > 0 && tot <= Cfg::XROWS;
             }
-            uint32_t lsum = lb;
+            // the block's 14 lists lie back to back in global memory (coords.cu): one copy; lane w keeps where list w starts
+            uint32_t lend = lb;
 #pragma unroll
-            for (int o = 16; o; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+            for (int o = 1; o < 16; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, lend, o);
+                if (lane >= o) lend += v;
+            }
+            const uint32_t lsum = __shfl_sync(0xffffffffu, lend, BW3_NW - 1);
             if (vt >= NST) mbar_wait(&empty[st], ((vt / NST) - 1) & 1);   // every consumer warp is done with virtual tile vt - NST
+            if (lane < BW3_NW) s_plan[st][4 + lane] = (int)(lend - lb);
+            __syncwarp();   // lane 0's arrive below publishes these stores with its own
             if (lane == 0) {
                 s_plan[st][0] = pl.ok ? pl.delta(0) : 0, s_plan[st][1] = pl.ok ? pl.delta(1) : 0, s_plan[st][2] = pl.ok ? pl.delta(2) : 0;
                 s_plan[st][3] = pl.ok;
                 const uint32_t dyb = (uint32_t)nrow * DLD * 4u;
                 mbar_arrive_expect_tx(&full[st], dyb + lsum + (MODE != 1 ? pl.bytes(CIN) : 0u));
                 bulk_g2s(sb, a.dy.p + g * a.dy.gs + a.dy.off + row0 * DLD, dyb, &full[st]);
+                if (lsum) bulk_g2s(sb + Cfg::DYB + Cfg::XS, a.map.pair_list + (tile0 + t) * PAIR_TILE_ENTRIES + blockIdx.x * PAIR_HALF_ENTRIES, lsum, &full[st]);
                 if constexpr (MODE != 1) issue_ranges(pl, a.x.p + g * a.x.gs + a.x.off, CIN, reinterpret_cast<float *>(sb + Cfg::DYB), &full[st]);
             }
-            __syncwarp();   // the barrier is armed before any other lane's copy can complete on it
-            if (lb) bulk_g2s(sb + Cfg::DYB + Cfg::XS + lane * 1024, a.map.pair_list + ((tile0 + t) * 27 + my_slot) * 256, lb, &full[st]);
             lb = lb_next, rv = rv_next;
         }
         return;
@@ -958,7 +962,7 @@ __global__ void __launch_bounds__(32 * (BW3_NW + 1), 1) conv27_bwd_w3_kernel(con
             // the offset's neighbour range) are folded into four bases, so a pair costs a shift/mask and an add per row.
             constexpr int DSH = (DLD == 8) ? 5 : 4, XSH = (CIN == 8) ? 5 : 4;
             const int dlt = s_plan[st][dxi];
-            const uint32_t a_l = smem_u32(sb + Cfg::DYB + Cfg::XS) + (uint32_t)(warp * 256 + lane) * 4u;
+            const uint32_t a_l = smem_u32(sb + Cfg::DYB + Cfg::XS) + (uint32_t)s_plan[st][4 + warp] + (uint32_t)lane * 4u;
             const uint32_t a_d0 = smem_u32(sdy) + dh0 * 4u, a_d1 = smem_u32(sdy) + dh1 * 4u;
             const uint32_t a_x = smem_u32(sb + Cfg::DYB) + ((uint32_t)dlt << XSH);
             const uint32_t a_x0 = a_x + xh0 * 4u, a_x1 = a_x + xh1 * 4u;
@@ -992,7 +996,7 @@ __global__ void __launch_bounds__(32 * (BW3_NW + 1), 1) conv27_bwd_w3_kernel(con
             }
         } else {
             // the neighbour ranges of this tile did not fit the staging area: gather x through L1
-            const uint32_t *lst = reinterpret_cast<const uint32_t *>(sb + Cfg::DYB + Cfg::XS) + warp * 256;
+            const uint32_t *lst = reinterpret_cast<const uint32_t *>(sb + Cfg::DYB + Cfg::XS + s_plan[st][4 + warp]);
             const float *xg = (MODE == 1) ? nullptr : (a.x.p + g * a.x.gs + a.x.off);
 #pragma unroll 1
             for (int b = 0; b < cnt; b += 32) {

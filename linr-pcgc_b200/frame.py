@@ -41,7 +41,7 @@ class RowTables:
     nbr27: Optional[torch.Tensor] = None
     tile_rng: Optional[torch.Tensor] = None   # int32 [ceil(R/128),6]: neighbour row ranges per tile (linr_tile_ranges)
     pair_cnt: Optional[torch.Tensor] = None   # int32 [ceil(R/256),32] and
-    pair_list: Optional[torch.Tensor] = None  # int32 [ceil(R/256),27,256]: existing (row, neighbour) pairs per tile and offset
+    pair_list: Optional[torch.Tensor] = None  # int32 [ceil(R/256),27*256]: existing (row, neighbour) pairs per tile and offset (layout: linr_b200.h)
     table: Optional[torch.Tensor] = None   # open-addressing hash (kept only on request)
     cap: int = 0
     _rows: Optional[Rows] = field(default=None, repr=False)
@@ -94,7 +94,7 @@ def build_tables(coords: torch.Tensor, scale: torch.Tensor, occ: Optional[torch.
         if n < (1 << 24):
             nt = (n + 255) // 256
             t.pair_cnt = torch.empty((nt, 32), dtype=torch.int32, device=dev)
-            t.pair_list = torch.empty((nt, 27, 256), dtype=torch.int32, device=dev)
+            t.pair_list = torch.empty((nt, 27 * 256), dtype=torch.int32, device=dev)
             rows = t.rows()
             check(lib.linr_pair_lists(C.byref(rows), ptr(t.pair_cnt), ptr(t.pair_list), s), "linr_pair_lists")
     return t

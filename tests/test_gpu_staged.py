@@ -80,20 +80,30 @@ def test_pair_lists_bit_exact(L, name):
     nb = _dense_from_compact(t.anchor, t.mask, n)
     cnt = t.pair_cnt.cpu().numpy()
     lst = t.pair_list.cpu().numpy().view(np.uint32)
-    assert cnt.shape == ((n + 255) // 256, 32) and lst.shape == ((n + 255) // 256, 27, 256)
+    assert cnt.shape == ((n + 255) // 256, 32) and lst.shape == ((n + 255) // 256, 27 * 256)
+    import ctypes
+    order = (ctypes.c_int32 * 28)()
+    L.lib.load().linr_pair_list_order(order)
+    order = np.array(order).reshape(2, 14)
+    assert sorted(order.reshape(-1).tolist()) == list(range(28))        # every offset once, 27 = the bias slot (no list)
     grouped = total = 0
     for ti in range(cnt.shape[0]):
         blk = nb[ti * 256:(ti + 1) * 256]
-        for k in range(27):
-            rl = np.nonzero(blk[:, k] >= 0)[0]
-            assert cnt[ti, k] == len(rl)
-            perm, nh = _pair_order(rl, blk[rl, k])
-            want = (rl[perm].astype(np.uint32) << np.uint32(24)) | blk[rl[perm], k].astype(np.uint32)
-            np.testing.assert_array_equal(lst[ti, k, :len(rl)], want)
-            got = lst[ti, k, :nh].reshape(-1, 4)
-            assert (np.sort((got >> np.uint32(24)) & 3, axis=1) == np.arange(4)).all()     # rows distinct modulo 4
-            assert (np.sort(got & np.uint32(3), axis=1) == np.arange(4)).all()             # neighbours too
-            grouped, total = grouped + nh, total + len(rl)
+        for h in range(2):
+            start = h * 14 * 256                                        # half h of the tile's storage, lists back to back
+            for k in order[h]:
+                if k == 27:
+                    continue
+                rl = np.nonzero(blk[:, k] >= 0)[0]
+                assert cnt[ti, k] == len(rl)
+                perm, nh = _pair_order(rl, blk[rl, k])
+                want = (rl[perm].astype(np.uint32) << np.uint32(24)) | blk[rl[perm], k].astype(np.uint32)
+                np.testing.assert_array_equal(lst[ti, start:start + len(rl)], want)
+                got = lst[ti, start:start + nh].reshape(-1, 4)
+                assert (np.sort((got >> np.uint32(24)) & 3, axis=1) == np.arange(4)).all()     # rows distinct modulo 4
+                assert (np.sort(got & np.uint32(3), axis=1) == np.arange(4)).all()             # neighbours too
+                grouped, total = grouped + nh, total + len(rl)
+                start += (len(rl) + 3) & ~3                             # every list starts on a multiple of 4 entries
         assert (cnt[ti, 27:] == 0).all()
     if name == "mid":
         assert grouped >= 0.6 * total
