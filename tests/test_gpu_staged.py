@@ -139,6 +139,23 @@ def test_weight_gradient_v3_matches_v2_and_is_reproducible(L):
                 assert (dW.double() - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("env", [{"LINR_BW3_MASK": "15"}, {"LINR_BW3_MASK": "15", "LINR_BW3_NOX": "1"}, {"LINR_BW3_MASK": "0"}])
+def test_weight_gradient_v3_switches(L, env):
+    """Every class on the staged kernel (4->4 included), the un-staged neighbour path of a tile whose ranges do not fit,
+    and the kernel switched off: same gradients up to fp32 re-association, bitwise reproducible run to run."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tests", "_bw3_variants_driver.py")], capture_output=True, text=True,
+                       timeout=600, cwd=root, env={**os.environ, **env})
+    assert p.returncode == 0, p.stderr[-3000:]
+    r = json.loads([l for l in p.stdout.splitlines() if l.startswith("RESULT ")][-1][len("RESULT "):])
+    assert r["repro"]
+    assert r["conv"] <= 2e-5 and r["net"] <= 5e-5, r
+
+
 def test_network_staged_vs_gathered(L, O):
     """Whole network: probabilities / CDFs bit-identical, gradient within fp32 re-association, training forward too."""
     g, S, sd, flat, fr = _net_case(L, O)
