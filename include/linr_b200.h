@@ -62,6 +62,15 @@ int linr_ctx_set_current(linr_ctx *ctx);
 int linr_ctx_hint_same_params(linr_ctx *ctx);
 int64_t linr_ctx_bank_calls(const linr_ctx *ctx);
 int64_t linr_ctx_bank_launches(const linr_ctx *ctx);
+/* Second stream of a context (no reference counterpart: autograd runs the reference's backward on one stream,
+ * main.py:316).  A training call made through an explicit context runs the kernels nothing in the call depends on -- the
+ * weight-gradient launches of linr_net_backward(_stages), the bit-input ConvA of the LDFE blocks in the training forward --
+ * on a stream owned by the context, forked from and joined to the caller's stream by events inside the call: when the
+ * call returns, everything it launched is ordered before later work on the caller's stream, as without it.  The results
+ * are bit-identical either way (same kernels, same partial sums).  linr_side_stream_enable(0) keeps every launch on
+ * the caller's stream (process-wide switch, returns the previous setting; also LINR_NO_SIDE_STREAM=1): bench.py uses
+ * it to time kernel classes one at a time. */
+int linr_side_stream_enable(int on);
 
 /* Launch accounting / live kernel timing (no reference counterpart: the reference has no profiler hooks,
  * SURVEY.md section 5).  Kernel classes are the K_* values of csrc/prof.cuh; linr_prof_name() names them.

@@ -37,6 +37,7 @@ SIGNATURES = {
     "linr_ctx_hint_same_params": (_I, [_P]),
     "linr_ctx_bank_calls": (_I64, [_P]),
     "linr_ctx_bank_launches": (_I64, [_P]),
+    "linr_side_stream_enable": (_I, [_I]),
     "linr_prof_enable": (_I, [C.c_uint32]),
     "linr_prof_read": (_I, [_I, C.POINTER(C.c_double), C.POINTER(_I64), C.POINTER(_I64)]),
     "linr_prof_classes": (_I, []),

@@ -291,6 +291,12 @@ struct linr_ctx {
     std::atomic<int64_t> bank_calls{0};       // training calls that held the bank
     int same_params = 0;                      // one-shot hint: the next training call sees the parameters of the previous one
     bool staged[2] = {false, false};          // forward / backward weight layouts of those parameters are in the staging area
+    // second stream of a backward call: the weight-gradient launches (leaves of the dependency graph) run beside the
+    // grad-input chain.  Made on first use; fork events are reused round robin (SideLane below).
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork_ev[32] = {nullptr};
+    cudaEvent_t join_ev = nullptr;
+    int fork_next = 0;
 };
 namespace {
 struct BankState {
@@ -379,6 +385,55 @@ struct BankScope {
         if (t_bank && t_bank->have_bank) bank_release(t_bank->stream);
         t_bank = nullptr;
     }
+};
+
+// The weight-gradient launches of a backward call produce chunk partials that nothing reads before the final reduction:
+// they run on the context's second stream, each behind an event recorded on the caller's stream after the kernel that
+// made its inputs, and the caller's stream waits for them once, before the call returns (or before the reduction).  They
+// read no constant-bank weights, so the bank's fills stay ordered on the caller's stream.  Only explicit contexts
+// (linr_ctx_create) have a second stream; LINR_NO_SIDE_STREAM=1 keeps everything on the caller's stream.
+std::atomic<int> g_side_on{1};
+struct SideLane {
+    cudaStream_t main = nullptr, side = nullptr;
+    linr_ctx *ctx = nullptr;
+    bool used = false;
+    explicit SideLane(cudaStream_t s) : main(s) {
+        static const bool off = getenv("LINR_NO_SIDE_STREAM") != nullptr;
+        linr_ctx *c = current_ctx();
+        if (off || c->is_default || !g_side_on.load(std::memory_order_relaxed)) return;
+        if (!c->side) {
+            if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess) {
+                cudaGetLastError();
+                c->side = nullptr;
+                return;
+            }
+            bool ok = cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming) == cudaSuccess;
+            for (auto &e : c->fork_ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+            if (!ok) {
+                cudaGetLastError();
+                return;   // half-made: side stays unused (destroy frees what exists)
+            }
+        }
+        if (!c->join_ev || !c->fork_ev[31]) return;
+        ctx = c, side = c->side;
+    }
+    // stream for a leaf launch whose inputs are complete on the caller's stream at this point
+    cudaStream_t leaf() {
+        if (!side) return main;
+        cudaEvent_t e = ctx->fork_ev[ctx->fork_next];
+        ctx->fork_next = (ctx->fork_next + 1) & 31;
+        cudaEventRecord(e, main);
+        cudaStreamWaitEvent(side, e, 0);
+        used = true;
+        return side;
+    }
+    void join() {
+        if (!used) return;
+        cudaEventRecord(ctx->join_ev, side);
+        cudaStreamWaitEvent(main, ctx->join_ev, 0);
+        used = false;
+    }
+    ~SideLane() { join(); }
 };
 
 // dynamic shared memory above 48 KB has to be opted into once per function and device (`done`: the caller's flags
@@ -569,7 +624,7 @@ void launch_pw_bwd_w(int64_t R, const NetWs &w, int P, const int *w_off, const i
 // Backward of ConvB and of the five inner layers for G blocks.  dout: gradient wrt the block output; leaves the
 // gradient wrt ConvA's (post-ReLU) output in gr.dy for block_A_backward.
 void block_Bmid_backward(const float *params, const BlockL *L, int G, const RowMap &m, const NetWs &w, int P, const BlockBufs &b,
-                         const BlockGrads &gr, Tens dout, cudaStream_t s) {
+                         const BlockGrads &gr, Tens dout, cudaStream_t s, SideLane &sl) {
     const int64_t R = m.n_rows;
     int wo[MAXG], bo[MAXG];
     auto offs = [&](int BlockL::*pw, int BlockL::*pb) {
@@ -581,7 +636,7 @@ void block_Bmid_backward(const float *params, const BlockL *L, int G, const RowM
 
     // ConvB: dW, then dz = B^T dout; its epilogue also applies conv1_2^T (k=1): dt2 = [t2 > 0](dz[:, 4:8] @ W12^T)
     offs(&BlockL::B_w, &BlockL::B_b);
-    launch_bwd_w<8, 8, 0>(m, w, P, wo, bo, G, z, dout, nullptr, 0, 0, s);
+    launch_bwd_w<8, 8, 0>(m, w, P, wo, bo, G, z, dout, nullptr, 0, 0, sl.leaf());
     {
         ConvArgs a = conv_args(m, params);
         for (int g = 0; g < G; ++g) a.w_off[g] = L[g].B_w, a.pw_w_off[g] = L[g].c12_w, a.pw_b_off[g] = -1;
@@ -591,9 +646,12 @@ void block_Bmid_backward(const float *params, const BlockL *L, int G, const RowM
     }
     // path 1 first (its dt1 is needed by the fused epilogue of conv0_0^T): conv1_2 (k=1) weights, conv1_1, conv1_0
     offs(&BlockL::c12_w, &BlockL::c12_b);
-    launch_pw_bwd_w<4, 4>(R, w, P, wo, bo, G, t2, dzh, s);
-    offs(&BlockL::c11_w, &BlockL::c11_b);
-    launch_bwd_w<4, 4, 0>(m, w, P, wo, bo, G, t1, dt2, nullptr, 0, 0, s);
+    {
+        cudaStream_t l = sl.leaf();   // one fork for the two: both inputs are complete here
+        launch_pw_bwd_w<4, 4>(R, w, P, wo, bo, G, t2, dzh, l);
+        offs(&BlockL::c11_w, &BlockL::c11_b);
+        launch_bwd_w<4, 4, 0>(m, w, P, wo, bo, G, t1, dt2, nullptr, 0, 0, l);
+    }
     {
         ConvArgs a = conv_args(m, params);
         for (int g = 0; g < G; ++g) a.w_off[g] = L[g].c11_w;
@@ -601,10 +659,13 @@ void block_Bmid_backward(const float *params, const BlockL *L, int G, const RowM
         launch_conv<4, 4, 0>(a, G, s);
     }
     offs(&BlockL::c10_w, &BlockL::c10_b);
-    launch_pw_bwd_w<8, 4>(R, w, P, wo, bo, G, y, dt1, s);
-    // path 0: conv0_1 then conv0_0
-    offs(&BlockL::c01_w, &BlockL::c01_b);
-    launch_bwd_w<4, 4, 0>(m, w, P, wo, bo, G, t0, dzl, nullptr, 0, 0, s);
+    {
+        cudaStream_t l = sl.leaf();
+        launch_pw_bwd_w<8, 4>(R, w, P, wo, bo, G, y, dt1, l);
+        // path 0: conv0_1 then conv0_0
+        offs(&BlockL::c01_w, &BlockL::c01_b);
+        launch_bwd_w<4, 4, 0>(m, w, P, wo, bo, G, t0, dzl, nullptr, 0, 0, l);
+    }
     {
         ConvArgs a = conv_args(m, params);
         for (int g = 0; g < G; ++g) a.w_off[g] = L[g].c01_w;
@@ -612,7 +673,7 @@ void block_Bmid_backward(const float *params, const BlockL *L, int G, const RowM
         launch_conv<4, 4, 0>(a, G, s);
     }
     offs(&BlockL::c00_w, &BlockL::c00_b);
-    launch_bwd_w<8, 4, 0>(m, w, P, wo, bo, G, y, dt0, nullptr, 0, 0, s);
+    launch_bwd_w<8, 4, 0>(m, w, P, wo, bo, G, y, dt0, nullptr, 0, 0, sl.leaf());
     {  // dy = [y > 0](dz (residual) + c00^T dt0 + dt1 @ W10^T): conv1_0^T (k=1) is applied in the epilogue
         ConvArgs a = conv_args(m, params);
         for (int g = 0; g < G; ++g) a.w_off[g] = L[g].c00_w, a.pw_w_off[g] = L[g].c10_w, a.pw_b_off[g] = -1;
@@ -624,11 +685,11 @@ void block_Bmid_backward(const float *params, const BlockL *L, int G, const RowM
 
 // Backward of ConvA for G blocks: weight gradient from (x | occupancy bits, dy); input gradient only if dx.p != null.
 void block_A_backward(const float *params, const BlockL *L, int G, const RowMap &m, const NetWs &w, int P, bool in_bits,
-                      const uint8_t *occ, int cin_base, int cin_step, Tens x, Tens dy, Tens dx, cudaStream_t s) {
+                      const uint8_t *occ, int cin_base, int cin_step, Tens x, Tens dy, Tens dx, cudaStream_t s, SideLane &sl) {
     int wo[MAXG], bo[MAXG];
     for (int g = 0; g < G; ++g) wo[g] = L[g].A_w, bo[g] = L[g].A_b;
-    if (in_bits) launch_bwd_w<8, 8, 1>(m, w, P, wo, bo, G, TN(), dy, occ, cin_base, cin_step, s);
-    else launch_bwd_w<8, 8, 0>(m, w, P, wo, bo, G, x, dy, nullptr, 0, 0, s);
+    if (in_bits) launch_bwd_w<8, 8, 1>(m, w, P, wo, bo, G, TN(), dy, occ, cin_base, cin_step, sl.leaf());
+    else launch_bwd_w<8, 8, 0>(m, w, P, wo, bo, G, x, dy, nullptr, 0, 0, sl.leaf());
     if (dx.p) {
         ConvArgs a = conv_args(m, params);
         for (int g = 0; g < G; ++g) a.w_off[g] = L[g].A_w;
@@ -726,6 +787,13 @@ static int net_forward_impl(const float *d_params, int scale_num, const linr_row
     BankCtx bank_ctx;
     BankScope bank_scope;
     if (train) bank_begin(bank_ctx, L, d_params, w.stage, 0, 4, s);   // training forward: weights via the constant bank
+    // ConvA of the LDFE blocks reads occupancy bits only (teacher forcing) and its weights from shared memory: in a
+    // training call it runs on the context's second stream beside SCE + ConvA of block_in
+    SideLane sl(s);
+    const bool a_bits = (phases & FWD_PRE) && jh > jl;
+    const bool a_bits_side = a_bits && train && (phases & FWD_GDFE);
+    if (a_bits_side)
+        block_A_forward(d_params, L.ob + jl, jh - jl, m, true, rows->d_occ, jl + 1, 1, TN(), w.ob_y + jl * R * 8, w.ob_t1 + jl * R * 4, sl.leaf());
     if (phases & FWD_GDFE) {
         {  // SCE
             SceArgs a = sce_args(d_params, L, rows);
@@ -736,8 +804,9 @@ static int net_forward_impl(const float *d_params, int scale_num, const linr_row
         // g = block_in(f0) -> hh[0] (group 7 of the block activation arrays)
         block_A_forward(d_params, &L.bin, 1, m, false, nullptr, 0, 0, T(w.f0, 0, 8), w.bi_y, w.bi_t1, s);
     }
-    if ((phases & FWD_PRE) && jh > jl)   // ConvA of the LDFE blocks (occupancy bits, teacher forcing)
+    if (a_bits && !a_bits_side)   // ConvA of the LDFE blocks (occupancy bits, teacher forcing)
         block_A_forward(d_params, L.ob + jl, jh - jl, m, true, rows->d_occ, jl + 1, 1, TN(), w.ob_y + jl * R * 8, w.ob_t1 + jl * R * 4, s);
+    sl.join();
     // the five inner layers of the blocks in multi-group launches
     {
         const bool gd = phases & FWD_GDFE, pre = (phases & FWD_PRE) && jh > jl;
@@ -789,10 +858,11 @@ static int net_backward_impl(const float *d_params, int scale_num, const linr_ro
     BankScope bank_scope;
     if (phases & (BWD_HEADS | BWD_LDFE | BWD_GDFE)) bank_begin(bank_ctx, L, d_params, w.stage, 4, 8, s);
     BlockGrads gr{w.g_dz, w.g_dt0, w.g_dy, w.g_dt2, w.g_dt1};
+    SideLane sl(s);
     auto blocks_backward = [&](int first, int count) {
         BlockGrads g2{gr.dz + first * R * 8, gr.dt0 + first * R * 4, gr.dy + first * R * 8, gr.dt2 + first * R * 4, gr.dt1 + first * R * 4};
         // output gradients: dhh[j+1] for LDFE block j, dg = dhh[8] for block_in = group 7
-        block_Bmid_backward(d_params, L.blk8 + first, count, m, w, P, bufs_at(w, first), g2, T(w.dhh + (first + 1) * R * 8, R * 8, 8), s);
+        block_Bmid_backward(d_params, L.blk8 + first, count, m, w, P, bufs_at(w, first), g2, T(w.dhh + (first + 1) * R * 8, R * 8, 8), s, sl);
     };
     if (phases & BWD_HEADS) {
         // heads: dc, MLP weight partials, SConv weight partials, dh_k
@@ -810,10 +880,13 @@ static int net_backward_impl(const float *d_params, int scale_num, const linr_ro
             head_bwd_rows_kernel<<<dim3((unsigned)ceil_div64(R, 128 * HEAD_RPT), (unsigned)G), 128, 0, s>>>(a);
         }
         {
-            ProfScope prof(K_HEADBWD, R * G, s);
-            head_bwd_w_kernel<<<dim3((unsigned)w.n_chunks, (unsigned)G), 256, 0, s>>>(a);
+            cudaStream_t l = sl.leaf();
+            {
+                ProfScope prof(K_HEADBWD, R * G, l);
+                head_bwd_w_kernel<<<dim3((unsigned)w.n_chunks, (unsigned)G), 256, 0, l>>>(a);
+            }
+            launch_bwd_w<8, 8, 0>(m, w, P, L.pr_w + lo, L.pr_b + lo, G, T(w.hh + lo * R * 8, R * 8, 8), T(w.dc + lo * R * 8, R * 8, 8), nullptr, 0, 0, l);
         }
-        launch_bwd_w<8, 8, 0>(m, w, P, L.pr_w + lo, L.pr_b + lo, G, T(w.hh + lo * R * 8, R * 8, 8), T(w.dc + lo * R * 8, R * 8, 8), nullptr, 0, 0, s);
         {
             ConvArgs ca = conv_args(m, d_params);
             for (int g = 0; g < G; ++g) ca.w_off[g] = L.pr_w[lo + g];
@@ -833,15 +906,16 @@ static int net_backward_impl(const float *d_params, int scale_num, const linr_ro
         else if (gd) blocks_backward(7, 1);
         // ConvA: LDFE blocks read occupancy bits (no input gradient); block_in propagates to f0
         if (ld)
-            block_A_backward(d_params, L.ob + jl, jh - jl, m, w, P, true, rows->d_occ, jl + 1, 1, TN(), T(w.g_dy + jl * R * 8, R * 8, 8), TN(), s);
+            block_A_backward(d_params, L.ob + jl, jh - jl, m, w, P, true, rows->d_occ, jl + 1, 1, TN(), T(w.g_dy + jl * R * 8, R * 8, 8), TN(), s, sl);
         if (gd) {
-            block_A_backward(d_params, &L.bin, 1, m, w, P, false, nullptr, 0, 0, T(w.f0, 0, 8), T(w.g_dy + 7 * R * 8, 0, 8), T(w.df0, 0, 8), s);
+            block_A_backward(d_params, &L.bin, 1, m, w, P, false, nullptr, 0, 0, T(w.f0, 0, 8), T(w.g_dy + 7 * R * 8, 0, 8), T(w.df0, 0, 8), s, sl);
             SceArgs sa = sce_args(d_params, L, rows);
             sa.df0 = T(w.df0, 0, 8), sa.chunk = w.chunk;
             ProfScope prof(K_SCE, R, s);
             sce_bwd_kernel<<<(unsigned)w.n_chunks, SCE_BWD_TPB, 0, s>>>(sa, w.sce_rec);
         }
     }
+    sl.join();   // the chunk partials of the weight gradients are complete on the caller's stream from here
     if (phases & BWD_FINAL) {
         if (own_gdfe) {
             SceArgs sa = sce_args(d_params, L, rows);
@@ -911,6 +985,13 @@ int linr_ctx_destroy(linr_ctx *ctx) {
         }
     }
     if (ctx->done) cudaEventDestroy(ctx->done);
+    if (ctx->side) {
+        cudaStreamSynchronize(ctx->side);
+        cudaStreamDestroy(ctx->side);
+    }
+    if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
+    for (auto &e : ctx->fork_ev)
+        if (e) cudaEventDestroy(e);
     delete ctx;
     return LINR_OK;
 }
@@ -922,6 +1003,7 @@ int linr_ctx_hint_same_params(linr_ctx *ctx) {
     (ctx ? ctx : current_ctx())->same_params = 1;
     return LINR_OK;
 }
+int linr_side_stream_enable(int on) { return g_side_on.exchange(on ? 1 : 0); }
 int64_t linr_ctx_bank_calls(const linr_ctx *ctx) {
     const linr_ctx *c = ctx ? ctx : current_ctx();
     return c->bank_calls.load(std::memory_order_relaxed);

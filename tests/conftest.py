@@ -7,6 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # as the package sets it; here before anything touches CUDA
 
 
 def pytest_configure(config):

@@ -479,6 +479,45 @@ def test_contexts_take_turns_at_the_weight_bank(L, O):
     b.close(), c.close()
 
 
+def test_second_stream_changes_no_bit(L, O):
+    """linr_side_stream_enable (include/linr_b200.h): the weight-gradient launches of a backward call and the bit-input
+    ConvA of a training forward run on the context's second stream, forked from / joined to the caller's stream inside
+    the call.  Same kernels, same partial sums: bits, gradient and the parameters after several optimiser steps on
+    frames that reuse one workspace are bitwise those of the one-stream schedule -- also when the caller's stream is
+    not the default stream and other work is queued behind the call."""
+    lib = L.lib.load()
+    pts = L.synth.make_sequence("tiny", 3)
+    frames = [L.frame.prepare_frame(p.cuda(), None, 64) for p in pts]
+    S = frames[0].n_scales
+    mr = max(f.tables.n_rows for f in frames)
+
+    def run(on, stream=None):
+        prev = lib.linr_side_stream_enable(1 if on else 0)
+        try:
+            with torch.cuda.stream(stream or torch.cuda.current_stream()):
+                tr = L.trainer.GopTrainer(S, "cuda", seed=11, max_rows=mr)
+                bits, grads = [], []
+                for it in range(6):
+                    fr = frames[it % 3]
+                    out = tr.runner.forward(tr.state.params, fr.tables, train=True, loss_scale=1.0 / fr.point_num)
+                    tr.runner.backward(tr.state.params, fr.tables, tr.grad)
+                    bits.append(out["bits"].clone()), grads.append(tr.grad.clone())   # queued right behind the call
+                    tr.step(fr)
+                res = (torch.stack(bits), torch.stack(grads), tr.state.params.clone())
+                tr.runner.close()
+            torch.cuda.synchronize()
+            return res
+        finally:
+            lib.linr_side_stream_enable(prev)
+
+    base = run(False)
+    other = torch.cuda.Stream()
+    other.wait_stream(torch.cuda.current_stream())
+    for res in (run(True), run(True, other), run(True)):
+        for a, b in zip(base, res):
+            assert torch.equal(a, b)
+
+
 def test_two_trainers_in_two_host_threads_match_serial_runs(L, O):
     """The constant weight bank is owned by one (host thread, stream) pair; a second trainer running concurrently in
     another host thread -- even on the same stream -- must fall back to the shared-memory kernels and still produce
