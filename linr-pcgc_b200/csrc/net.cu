@@ -401,6 +401,8 @@ struct SideLane {
         static const bool off = getenv("LINR_NO_SIDE_STREAM") != nullptr;
         linr_ctx *c = current_ctx();
         if (off || c->is_default || !g_side_on.load(std::memory_order_relaxed)) return;
+        int dev = -1;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev != c->device) return;   // the context's streams live on its device
         if (!c->side) {
             if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess) {
                 cudaGetLastError();
