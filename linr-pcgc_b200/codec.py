@@ -230,7 +230,7 @@ def decode_frames(params: torch.Tensor, scale_num: int, jobs: Sequence, workers:
 _POPC = {}
 
 
-def decode_frames_batched(params: torch.Tensor, scale_num: int, jobs: Sequence, max_batch: int = 8, workers: int = 2,
+def decode_frames_batched(params: torch.Tensor, scale_num: int, jobs: Sequence, max_batch: int = 8, workers: Optional[int] = None,
                           threads: Optional[int] = None) -> List[torch.Tensor]:
     """Decode independent frames in LOCKSTEP (frames of a GOP only share the model): at every scale the parents of all
     frames of a batch are concatenated -- frame f shifted by f * stride in x, so the frames stay sorted, unique and out
@@ -239,7 +239,10 @@ def decode_frames_batched(params: torch.Tensor, scale_num: int, jobs: Sequence, 
     A batch makes 56 launch sets and device<->host round trips instead of 56 per frame, and the launches are large
     enough to fill the GPU (a per-frame stage of a coarse scale is a handful of blocks).  `workers` batches run at the
     same time on their own streams and host threads, so the network passes of one overlap the range decoding of the
-    other.  Bit-identical CDFs: a row sees the same neighbours in the same order as in its own frame.
+    others: four in flight when the host has the cores (measured, tools/decode_profile.py: 32 loot frames 3.40 ms/frame
+    with 2 batches of 8 in flight, 2.29 with 4; 16 MVUB-shaped frames 2.31 with 2 x 8, 2.07 with 4 x 4), and batches no
+    larger than it takes to have that many.  Bit-identical CDFs: a row sees the same neighbours in the same order as in
+    its own frame.
     jobs: (all_bytes, low_coords CUDA int32 [N,3])."""
     from concurrent.futures import ThreadPoolExecutor
     import threading
@@ -250,7 +253,9 @@ def decode_frames_batched(params: torch.Tensor, scale_num: int, jobs: Sequence, 
     s_max = max(len(j[0]) for j in jobs)
     low_stride = 1 << max(1, (low_max + 2 - 1).bit_length())                  # >= low_max + 2: a gap of at least one voxel
     fit = max(1, (1 << 20) // (low_stride << s_max))                          # coordinates stay below 2^20 at the finest level
-    B = max(1, min(max_batch, fit))
+    if workers is None:
+        workers = min(4, max(2, rc.host_cores() // 4))
+    B = max(1, min(max_batch, fit, -(-len(jobs) // workers)))
     batches = [list(range(b0, min(b0 + B, len(jobs)))) for b0 in range(0, len(jobs), B)]
     workers = max(1, min(workers, len(batches)))
     threads = threads or max(B, rc.host_cores() // workers)
