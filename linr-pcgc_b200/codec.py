@@ -82,15 +82,23 @@ def encode_frame(runner: NetRunner, params: torch.Tensor, frame: Frame, threads:
 
 
 def encode_frames(runner: NetRunner, params: torch.Tensor, frames: Sequence[Frame], threads: Optional[int] = None,
-                  depth: int = 4, coders: int = 2) -> List[List[bytes]]:
+                  depth: Optional[int] = None, coders: Optional[int] = None) -> List[List[bytes]]:
     """Encode several frames with the GPU and the host coder overlapped: while the range coder works on frame i
     (C code, GIL released), the network forward and the CDF download of frame i+1 are already running.  `depth` pinned
     staging sets bound the frames in flight, `coders` frames are range-coded at the same time (the 8 stage streams of
-    the finest scale hold 3/4 of a frame's symbols, so one frame cannot use more than ~8 cores).  Same bytes as
-    `encode_frame` frame by frame."""
+    the finest scale hold 3/4 of a frame's symbols, so one frame cannot use more than ~8 cores).  Defaults (measured,
+    tools/encode_profile.py, 16 host cores: 1.45 ms/frame with 2 coders x 8 threads, 1.31 with 3 x 8): three frames in the
+    coder when the host has >= 12 cores, else two; up to 8 threads each.  Same bytes as `encode_frame` frame by frame."""
     from concurrent.futures import ThreadPoolExecutor
     if not frames:
         return []
+    cores = rc.host_cores()
+    if coders is None:
+        coders = 3 if cores >= 12 else 2
+    if depth is None:
+        depth = 2 * coders
+    if threads is None:
+        threads = max(2, min(8, cores // 2))
     cap = max(f.tables.n_rows for f in frames)
     sets = [(torch.empty(8 * max(cap, 1), dtype=torch.int16).pin_memory(), torch.empty(max(cap, 1), dtype=torch.uint8).pin_memory())
             for _ in range(min(depth, len(frames)))]
@@ -110,7 +118,7 @@ def encode_frames(runner: NetRunner, params: torch.Tensor, frames: Sequence[Fram
                 cdfs.append(cdf[k, a:b])
                 syms.append(occ[a:b])
                 shifts.append(k)
-        streams = rc.encode_binary_batch(cdfs, syms, shifts, threads or max(2, rc.host_cores() // max(1, coders)))
+        streams = rc.encode_binary_batch(cdfs, syms, shifts, threads)
         return [pack_bitstream(streams[8 * s: 8 * s + 8]) for s in range(f.n_scales)]
 
     with ThreadPoolExecutor(max_workers=max(1, coders)) as pool:
