@@ -27,7 +27,10 @@ d["final_bytes"] = enc.model_bytes
 flat = model_compression.decompress_model(d, n, dev)
 lows, mins = codec.unpack_low_xyz(enc.low_enc_bytes)
 jobs = [(fb, torch.from_numpy(lows[i]).to(dev)) for i, fb in enumerate(enc.frame_bytes)]
-for mb, wk in ((8, 2), (8, 3), (8, 4), (4, 4), (16, 2), (6, 3), (4, 6), (11, 3)):
+sweep = ((8, 2), (8, 3), (8, 4), (4, 4), (16, 2), (6, 3), (4, 6), (11, 3))
+if len(sys.argv) > 4:
+    sweep = tuple(tuple(int(v) for v in a.split("x")) for a in sys.argv[4].split(","))
+for mb, wk in sweep:
     best = 1e9
     for _ in range(3):
         torch.cuda.synchronize()
