@@ -390,8 +390,20 @@ class Job:
         """One whole job; returns {gop: EncodedGop} for the GOPs whose group this rank leads."""
         cx, D = self.cx, self.cx.D
         out, state0 = {}, None
-        for g, ranks in self.mine:
-            frames = self.pipeline.prepare_gop(self.pts_host[g], self.S, 64, cx.dev) if from_host else self.frames[g]
+        bg_prep = from_host and os.environ.get("LINR_BENCH_BG_PREP", "1") != "0"
+        if bg_prep and not hasattr(self, "preparer"):
+            self.preparer = self.pipeline.GopPreparer(cx.dev)
+        for i, (g, ranks) in enumerate(self.mine):
+            if not from_host:
+                frames = self.frames[g]
+            elif not bg_prep:
+                frames = self.pipeline.prepare_gop(self.pts_host[g], self.S, 64, cx.dev)
+            else:
+                # end to end: the rank's first GOP is uploaded and prepared in line, every later one in the background
+                # (pipeline.GopPreparer) while the GOP before it is overfitted
+                frames = self.preparer.collect() if i > 0 else self.pipeline.prepare_gop(self.pts_host[g], self.S, 64, cx.dev)
+                if i + 1 < len(self.mine):
+                    self.preparer.submit(self.pts_host[self.mine[i + 1][0]], self.S, 64)
             tr = self.trainers[tuple(ranks)]
             if g == 0:
                 tr.reset(seed=8807)
@@ -484,7 +496,9 @@ def run_job(cx: Ctx, args, shape, G, K, W, e2e=True, with_checks=True):
                                  "ms_per_frame": d_ms, "table_bytes_per_frame": prep_bytes,
                                  "achieved": prep_bytes / max(d_ms, 1e-9) / 1e6, "unit": "GB/s", "peak": line["roofline"]["peak"] if line["roofline"] else None,
                                  "frac": (prep_bytes / max(d_ms, 1e-9) / 1e6) / line["roofline"]["peak"] if line["roofline"] else None,
-                                 "note": "table bytes written per frame / (e2e - resident) time; sort passes and hash probes re-read them several times"}
+                                 "note": "table bytes written per frame / (e2e - resident) time; sort passes and hash probes re-read them several times; "
+                                         "only a rank's first GOP is prepared in line, the later ones in the background while the GOP "
+                                         "before them is overfitted (pipeline.GopPreparer)"}
     # phase timings (one extra untimed-for-the-headline pass each): GOP 0's fit, whole-job fit, encode
     if with_checks:
         ms_fit, _, _ = cx.timed(lambda: job.step(encode=False), 1)

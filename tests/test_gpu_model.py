@@ -161,3 +161,39 @@ def test_cli_end_to_end_lossless(env, tmp_path):
     dec0 = pointio.read_ply(str(tmp_path / "dec" / "gop_2_3" / "frame0001_dec.ply"))
     src = pointio.read_ply(str(ori / "f003.ply"))
     assert (dec0 == src[np.lexsort((src[:, 2], src[:, 1], src[:, 0]))]).all()
+
+
+def test_background_gop_preparer_matches_in_line_preparation():
+    """pipeline.GopPreparer: the next GOP uploaded and prepared on a side stream / host thread while the caller works on
+    its own stream -- the same tables bit for bit as prepare_gop in line, usable on the caller's stream afterwards."""
+    import dataclasses
+    from linr_pcgc_b200 import pipeline, synth
+    from linr_pcgc_b200.trainer import GopTrainer
+    pts = [p.cpu().pin_memory() for p in synth.make_sequence("tiny", 4)]
+    ref = pipeline.prepare_gop(pts, None, 64, "cuda")
+    S = ref[0].n_scales
+    prep = pipeline.GopPreparer("cuda")
+    prep.submit(pts, S, 64)
+    tr = GopTrainer(S, "cuda", seed=3, max_rows=max(f.tables.n_rows for f in ref))
+    tr.fit(ref, 1)                                   # the caller's stream is busy meanwhile
+    got = prep.collect()
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        assert a.scale_off == b.scale_off and a.point_num == b.point_num and (a.coord_min == b.coord_min).all()
+        assert torch.equal(a.xyz, b.xyz)
+        for k in dataclasses.fields(a.tables):
+            x, y = getattr(a.tables, k.name), getattr(b.tables, k.name)
+            if not isinstance(x, torch.Tensor):
+                continue
+            if k.name == "anchor":       # defined where the column has a neighbour (the other words are never read)
+                n = a.tables.n_rows
+                for c in range(9):
+                    has = ((a.tables.mask.to(torch.int64) >> (3 * c)) & 7) != 0
+                    assert torch.equal(x[c, :n][has], y[c, :n][has]), "anchor"
+            elif k.name == "pair_list":  # entries beyond a list's length are padding
+                pass
+            else:
+                assert torch.equal(x, y), k.name
+    l0 = GopTrainer(S, "cuda", seed=5, max_rows=tr.runner.max_rows).fit(ref, 1)
+    l1 = GopTrainer(S, "cuda", seed=5, max_rows=tr.runner.max_rows).fit(got, 1)
+    assert l0 == l1                                  # and they train to the same bits
